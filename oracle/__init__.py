@@ -1,0 +1,169 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.
+
+ctypes binding of ``oracle/liboracle.so`` (the plain-C CPU restatement of the
+reference's hot path).  Only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import this
+package; nothing under ``sandstorm_b200/`` does.
+
+Elements are numpy ``uint64`` arrays of shape ``(..., 4)``: little-endian limbs
+of the Montgomery form x*2^256 mod p (reference: crypto/src/utils.rs:15-17).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+
+P = 2**251 + 17 * 2**192 + 1
+R = 2**256
+R_INV = pow(R, -1, P)
+GENERATOR = 3
+
+TREE_KECCAK, TREE_KECCAK_M20, TREE_FRIENDLY, TREE_BLAKE2S_M20, TREE_SHA256 = range(5)
+HASH_KECCAK, HASH_KECCAK_M20, HASH_BLAKE2S, HASH_BLAKE2S_M20, HASH_SHA256 = range(5)
+
+
+def build(force: bool = False) -> str:
+    """Compile liboracle.so in-tree (gcc, seconds)."""
+    if force or not os.path.exists(_LIB_PATH) or any(
+        os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB_PATH)
+        for f in os.listdir(_HERE)
+        if f.endswith((".c", ".h"))
+    ):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "liboracle.so"])
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        _lib = ctypes.CDLL(_LIB_PATH)
+    return _lib
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+# ----------------------------------------------------------------- conversions
+def to_mont(values) -> np.ndarray:
+    """Python ints (canonical) -> uint64[...,4] Montgomery limbs."""
+    vals = [int(v) % P * R % P for v in values]
+    out = np.empty((len(vals), 4), dtype=np.uint64)
+    for i, v in enumerate(vals):
+        for j in range(4):
+            out[i, j] = (v >> (64 * j)) & 0xFFFFFFFFFFFFFFFF
+    return out
+
+
+def from_mont(arr: np.ndarray) -> list[int]:
+    """uint64[...,4] Montgomery limbs -> Python ints (canonical)."""
+    flat = np.ascontiguousarray(arr, dtype=np.uint64).reshape(-1, 4)
+    out = []
+    for row in flat:
+        v = int(row[0]) | (int(row[1]) << 64) | (int(row[2]) << 128) | (int(row[3]) << 192)
+        out.append(v * R_INV % P)
+    return out
+
+
+def random_felts(rng: np.random.Generator, *shape: int) -> np.ndarray:
+    """Uniform-ish elements in [0,p) already in Montgomery form (any residue is a
+    valid Montgomery representative, so sampling the limbs directly is uniform)."""
+    n = int(np.prod(shape))
+    a = rng.integers(0, 2**64, size=(n, 4), dtype=np.uint64)
+    a[:, 3] &= np.uint64(0x07FFFFFFFFFFFFFF)     # < 2^251 < p
+    return a.reshape(*shape, 4)
+
+
+# ------------------------------------------------------------------------ field
+def fp_mul(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+    b = np.ascontiguousarray(b, dtype=np.uint64).reshape(-1, 4)
+    out = np.empty_like(a)
+    f = lib().fp_mul
+    for i in range(a.shape[0]):
+        f(_ptr(out[i]), _ptr(a[i]), _ptr(b[i]))
+    return out
+
+
+# -------------------------------------------------------------------------- NTT
+def ntt(cols: np.ndarray, inverse: bool = False) -> np.ndarray:
+    """cols: uint64[n_cols, n, 4]; per-column Radix2EvaluationDomain fft / ifft."""
+    a = np.array(cols, dtype=np.uint64, order="C", copy=True)
+    n_cols, n, _ = a.shape
+    log_n = n.bit_length() - 1
+    assert 1 << log_n == n
+    lib().oracle_ntt_fp252_batch(_ptr(a), ctypes.c_int(n_cols), ctypes.c_int(log_n), ctypes.c_int(int(inverse)))
+    return a
+
+
+def lde(cols: np.ndarray, log_blowup: int) -> np.ndarray:
+    """Matrix::interpolate then Matrix::evaluate on the coset 3*<w_N>."""
+    a = np.ascontiguousarray(cols, dtype=np.uint64)
+    n_cols, n, _ = a.shape
+    log_n = n.bit_length() - 1
+    out = np.empty((n_cols, n << log_blowup, 4), dtype=np.uint64)
+    lib().oracle_lde_fp252_batch(_ptr(a), ctypes.c_int(n_cols), ctypes.c_int(log_n), ctypes.c_int(log_blowup), _ptr(out))
+    return out
+
+
+def num_threads() -> int:
+    return int(lib().oracle_num_threads())
+
+
+# ----------------------------------------------------------------------- hashes
+def hash_bytes(kind: int, data: bytes) -> bytes:
+    out = ctypes.create_string_buffer(32)
+    lib().oracle_hash_bytes(ctypes.c_int(kind), data, ctypes.c_size_t(len(data)), out)
+    return out.raw
+
+
+def pedersen_hash(a: int, b: int) -> int:
+    am, bm = to_mont([a]), to_mont([b])
+    out = np.empty((1, 4), dtype=np.uint64)
+    lib().oracle_pedersen_hash(_ptr(out), _ptr(am), _ptr(bm))
+    return from_mont(out)[0]
+
+
+def pedersen_hash_mont(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+    b = np.ascontiguousarray(b, dtype=np.uint64).reshape(-1, 4)
+    out = np.empty_like(a)
+    f = lib().oracle_pedersen_hash
+    for i in range(a.shape[0]):
+        f(_ptr(out[i]), _ptr(a[i]), _ptr(b[i]))
+    return out
+
+
+def hash_rows(kind: int, cols: np.ndarray, bitrev_rows: bool = False) -> np.ndarray:
+    a = np.ascontiguousarray(cols, dtype=np.uint64)
+    n_cols, n, _ = a.shape
+    out = np.empty((n, 32), dtype=np.uint8)
+    lib().oracle_hash_rows(ctypes.c_int(kind), _ptr(a), ctypes.c_int(n_cols), ctypes.c_size_t(n), ctypes.c_int(int(bitrev_rows)), _ptr(out))
+    return out
+
+
+def merkle_build(kind: int, cols: np.ndarray, n_friendly: int = 22, bitrev_rows: bool = False):
+    """Returns (nodes uint8[n,32] with slot 0 unused, leaves uint8[n,32], root_bytes)."""
+    a = np.ascontiguousarray(cols, dtype=np.uint64)
+    n_cols, n, _ = a.shape
+    log_rows = n.bit_length() - 1
+    nodes = np.zeros((n, 32), dtype=np.uint8)
+    leaves = np.zeros((n, 32), dtype=np.uint8)
+    rc = lib().oracle_merkle_build(ctypes.c_int(kind), ctypes.c_int(n_friendly), _ptr(a), ctypes.c_int(n_cols),
+                                   ctypes.c_int(log_rows), ctypes.c_int(int(bitrev_rows)), _ptr(nodes), _ptr(leaves))
+    if rc != 0:
+        raise ValueError(f"oracle_merkle_build failed: {rc}")
+    root = ctypes.create_string_buffer(32)
+    lib().oracle_merkle_root_bytes(ctypes.c_int(kind), ctypes.c_int(n_friendly), ctypes.c_int(n_cols), ctypes.c_int(log_rows), _ptr(nodes), root)
+    return nodes, leaves, root.raw
