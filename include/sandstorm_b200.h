@@ -1,0 +1,143 @@
+/* sandstorm_b200 — C ABI of the B200 (sm_100a) proving backend.
+ *
+ * This is the drop-in boundary for the ONE hot path of `sandstorm prove`:
+ * per-column LDE, Cairo-AIR constraint-composition evaluation, Merkle commitment, FRI folding,
+ * DEEP composition.  The reference (Rust) has no FFI of its own: the seam is the trait surface
+ * between sandstorm and ministark.  Each entry point below names the reference interface it
+ * replaces; INTEGRATION.md shows the Rust `extern "C"` block and trait impls that bind it.
+ *
+ * Conventions
+ *   - every function returns ss_status (0 = OK, < 0 = error; ss_last_error(ctx) has the text).
+ *     Nothing panics or throws across the ABI (the reference panics via unwrap(), e.g.
+ *     crypto/src/merkle/mod.rs:116,120 — the Rust shim maps a non-zero status to that panic).
+ *   - Fp252 element = 4 x u64 little-endian limbs of x*2^256 mod p, canonical (< p): the exact
+ *     bytes of ark-ff's Fp256<MontBackend<_,4>> that reference crypto/src/utils.rs:15-17 exposes.
+ *     Goldilocks element = 1 x u64 (see ss_field).
+ *   - matrices are column-major, one contiguous column of 2^log_rows elements every `col_stride`
+ *     elements: the layout of ministark::Matrix (Vec<GpuVec<F>>), SURVEY.md §8 a1.
+ *   - d_* pointers are device memory of the ctx's GPU, h_* pointers are host memory.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the ctx's own stream).  Calls are
+ *     asynchronous on that stream unless stated; one ss_ctx per (thread, device).
+ */
+#ifndef SANDSTORM_B200_H
+#define SANDSTORM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ss_ctx ss_ctx;
+typedef struct ss_tree ss_tree;
+
+typedef enum {
+    SS_OK = 0,
+    SS_ERR_INVALID = -1,      /* bad argument                                   */
+    SS_ERR_CUDA = -2,         /* CUDA runtime / launch failure                  */
+    SS_ERR_OOM = -3,          /* device allocation failed                       */
+    SS_ERR_UNSUPPORTED = -4   /* valid request this build does not implement    */
+} ss_status;
+
+typedef enum {
+    SS_FIELD_FP252 = 0,       /* p = 2^251 + 17*2^192 + 1  (cli/src/main.rs:25-26)  */
+    SS_FIELD_GOLDILOCKS = 1   /* p = 2^64 - 2^32 + 1       (cli/src/main.rs:30)     */
+} ss_field;
+
+typedef enum {
+    SS_ORDER_NATURAL = 0,
+    SS_ORDER_BITREV = 1
+} ss_order;
+
+/* Which reference MatrixMerkleTree the commitment reproduces (src/claims.rs:10-32). */
+typedef enum {
+    SS_TREE_KECCAK = 0,        /* LeafVariantMerkleTree<Keccak256HashFn>            recursive::EthVerifierClaim  */
+    SS_TREE_KECCAK_M20 = 1,    /* LeafVariantMerkleTree<MaskedKeccak256HashFn<20>>  starknet::EthVerifierClaim   */
+    SS_TREE_FRIENDLY = 2,      /* FriendlyMerkleTree<N, PedersenHashFn>             *::CairoVerifierClaim        */
+    SS_TREE_BLAKE2S_M20 = 3,   /* masked Blake2s at every level (Friendly with N = 0)                            */
+    SS_TREE_SHA256 = 4         /* ministark MatrixMerkleTreeImpl<Sha256HashFn> (Goldilocks claims)               */
+} ss_tree_kind;
+
+/* ------------------------------------------------------------------ context / memory */
+int ss_version(void);
+ss_status ss_create(int device, ss_ctx **out);
+void ss_destroy(ss_ctx *ctx);
+const char *ss_last_error(const ss_ctx *ctx);
+ss_status ss_sync(ss_ctx *ctx);
+/* thin wrappers so that a host without the CUDA runtime (Rust) can own device buffers;
+ * replaces ministark_gpu's GpuAllocator / GpuVec role (layouts/src/recursive/trace.rs:55-56,115) */
+ss_status ss_malloc(ss_ctx *ctx, size_t bytes, void **d_ptr);
+ss_status ss_free(ss_ctx *ctx, void *d_ptr);
+ss_status ss_host_register(ss_ctx *ctx, void *h_ptr, size_t bytes);     /* pin a Vec for async copies */
+ss_status ss_host_unregister(ss_ctx *ctx, void *h_ptr);
+ss_status ss_memcpy_h2d(ss_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, void *stream);
+ss_status ss_memcpy_d2h(ss_ctx *ctx, void *h_dst, const void *d_src, size_t bytes, void *stream);
+
+/* ------------------------------------------------------------------ NTT / LDE (§8 a2, a3, a8)
+ * ss_ntt: per-column ark-poly Radix2EvaluationDomain::{fft, ifft, coset_fft, coset_ifft}
+ * (what ministark Matrix::interpolate / Matrix::evaluate run; domain generator 3^((p-1)/n),
+ * pinned by builtins/src/pedersen/periodic.rs:1184-1209; coset offset = Fp::GENERATOR = 3).
+ * In place on d_cols.  inverse includes the 1/n factor.  in/out_order let a caller skip the
+ * bit-reversal permutation (DIF: natural->bitrev, DIT: bitrev->natural are the native forms). */
+ss_status ss_ntt(ss_ctx *ctx, ss_field field, void *d_cols, uint64_t col_stride, int n_cols, int log_n,
+                 int inverse, int coset, ss_order in_order, ss_order out_order, void *stream);
+
+/* ss_lde: Matrix::interpolate(trace_domain) then Matrix::evaluate(lde_domain) fused:
+ * trace evaluations on <w_n>  ->  evaluations on 3*<w_N>, N = n << log_blowup.
+ * d_coeffs (optional, n per column, stride coeff_stride) receives the interpolated polynomials
+ * (coset-scaled: c_k * 3^k, BIT-REVERSED order) — the operand the DEEP / OOD stage consumes. */
+ss_status ss_lde(ss_ctx *ctx, ss_field field, const void *d_trace, uint64_t trace_stride, int n_cols,
+                 int log_n, int log_blowup, void *d_lde, uint64_t lde_stride, void *d_coeffs,
+                 uint64_t coeff_stride, ss_order out_order, void *stream);
+
+/* ------------------------------------------------------------------ Merkle (§8 a9-a13)
+ * ss_merkle_build = MatrixMerkleTree::from_matrix (crypto/src/merkle/mod.rs:110-123, :289-304):
+ * n_cols == 1 -> raw-leaf variant, n_cols >= 2 -> row hashes (crypto/src/merkle/utils.rs:19-46)
+ * then MerkleTreeImpl::new.  row_order = SS_ORDER_BITREV commits row brev(i) as leaf i (fused
+ * bit-reversal).  n_friendly = N_FRIENDLY_LAYERS (22 in src/claims.rs:10), SS_TREE_FRIENDLY only.
+ * The tree stays on the device until ss_tree_free (trees must outlive prove(), §8b ownership). */
+ss_status ss_merkle_build(ss_ctx *ctx, ss_tree_kind kind, int n_friendly, const void *d_cols,
+                          uint64_t col_stride, int n_cols, int log_rows, ss_order row_order,
+                          ss_tree **out, void *stream);
+/* MerkleTree::root -> Digest::as_bytes (32 bytes).  Synchronises. */
+ss_status ss_merkle_root(ss_ctx *ctx, const ss_tree *tree, uint8_t root[32]);
+/* Copies node i (1 = root .. 2^log_rows - 1; storage form: byte digest, or Montgomery limbs for
+ * algebraic levels) / leaf digests for MerkleTree::prove path extraction.  Synchronises. */
+ss_status ss_merkle_nodes(ss_ctx *ctx, const ss_tree *tree, const uint64_t *h_indices, size_t n,
+                          uint8_t *h_out /* n * 32 */);
+ss_status ss_merkle_leaves(ss_ctx *ctx, const ss_tree *tree, const uint64_t *h_indices, size_t n,
+                           uint8_t *h_out /* n * 32 */);
+/* MerkleTree::prove(indices): sibling path of each index, leaf level first (log_rows * 32 bytes each) */
+ss_status ss_merkle_open(ss_ctx *ctx, const ss_tree *tree, const uint64_t *h_indices, size_t n,
+                         uint8_t *h_paths /* n * log_rows * 32 */);
+int ss_tree_log_rows(const ss_tree *tree);
+void ss_tree_free(ss_tree *tree);
+/* batch Pedersen hash (builtins/src/pedersen/mod.rs:31-36), Montgomery limbs in and out */
+ss_status ss_pedersen_hash(ss_ctx *ctx, const void *d_a, const void *d_b, void *d_out, size_t n, void *stream);
+/* Matrix::read_row for the query phase: h_rows[i*n_cols + j] = cols[j][idx[i]].  Synchronises. */
+ss_status ss_rows_gather(ss_ctx *ctx, const void *d_cols, uint64_t col_stride, int n_cols,
+                         const uint64_t *h_indices, size_t n, void *h_rows);
+
+/* ------------------------------------------------------------------ FRI / DEEP (§8 a14, a15) */
+/* one radix-2^log_fold FRI fold of evaluations on offset*<w_N> (natural order) with challenge alpha:
+ * out[i] = sum_j alpha^j * f_j(x_i^(2^log_fold)),  out has N >> log_fold elements on the folded coset. */
+ss_status ss_fri_fold(ss_ctx *ctx, ss_field field, const void *d_evals, int log_n, int log_fold,
+                      const void *h_alpha, const void *h_domain_offset, void *d_out, void *stream);
+/* evaluate polynomials (coefficients as written by ss_lde: coset-scaled, bit-reversed) at points:
+ * h_out[i*n_cols + j] = poly_j(z_i)      (OOD evaluations).  Synchronises. */
+ss_status ss_poly_eval(ss_ctx *ctx, ss_field field, const void *d_coeffs, uint64_t coeff_stride, int n_cols,
+                       int log_n, const void *h_points, size_t n_points, void *h_out);
+
+/* ------------------------------------------------------------------ constraint evaluation (§8 a4-a7)
+ * Evaluates a compiled composition-constraint program (the Expr DAG of
+ * AirConfig::composition_constraint, layouts/src/recursive/air.rs:1184-1200, flattened by the host
+ * into straight-line code; format in sandstorm_b200/air/program.py) on every LDE row.          */
+ss_status ss_constraint_eval(ss_ctx *ctx, const void *h_program, size_t program_bytes,
+                             const void *d_lde_cols, uint64_t col_stride, int n_cols, int log_n,
+                             int log_blowup, void *d_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,120 @@
+// Context, memory helpers and error plumbing of the C ABI (include/sandstorm_b200.h).
+#include "ctx.h"
+
+using namespace ss;
+
+namespace ss {
+
+ss_status scratch_reserve(ss_ctx *ctx, size_t bytes, void **out) {
+    if (bytes > ctx->scratch_bytes) {
+        if (ctx->scratch) {
+            SS_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+            SS_CUDA_CHECK(ctx, cudaFree(ctx->scratch));
+            ctx->scratch = nullptr;
+            ctx->scratch_bytes = 0;
+        }
+        SS_CUDA_CHECK(ctx, cudaMalloc(&ctx->scratch, bytes));
+        ctx->scratch_bytes = bytes;
+    }
+    *out = ctx->scratch;
+    return SS_OK;
+}
+
+ss_status cached_table(ss_ctx *ctx, std::tuple<int, int, int> key, size_t n_elems,
+                       void (*fill)(Fp *dst, size_t n, int log_n, int variant), Fp **out) {
+    auto it = ctx->tables.find(key);
+    if (it != ctx->tables.end()) {
+        *out = static_cast<Fp *>(it->second);
+        return SS_OK;
+    }
+    std::vector<Fp> host(n_elems);
+    fill(host.data(), n_elems, std::get<1>(key), std::get<2>(key));
+    void *d = nullptr;
+    SS_CUDA_CHECK(ctx, cudaMalloc(&d, n_elems * sizeof(Fp)));
+    // synchronous copy: the pageable staging vector dies at scope exit
+    SS_CUDA_CHECK(ctx, cudaMemcpy(d, host.data(), n_elems * sizeof(Fp), cudaMemcpyHostToDevice));
+    ctx->tables[key] = d;
+    *out = static_cast<Fp *>(d);
+    return SS_OK;
+}
+
+}  // namespace ss
+
+extern "C" {
+
+int ss_version(void) { return 100; }
+
+ss_status ss_create(int device, ss_ctx **out) {
+    if (!out) return SS_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return SS_ERR_CUDA;   // fail loudly: no CPU fallback
+    if (device < 0 || device >= count) return SS_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return SS_ERR_CUDA;
+    ss_ctx *ctx = new ss_ctx();
+    ctx->device = device;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return SS_ERR_CUDA;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    *out = ctx;
+    return SS_OK;
+}
+
+void ss_destroy(ss_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &kv : ctx->tables) cudaFree(kv.second);
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *ss_last_error(const ss_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+ss_status ss_sync(ss_ctx *ctx) {
+    if (!ctx) return SS_ERR_INVALID;
+    SS_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return SS_OK;
+}
+
+ss_status ss_malloc(ss_ctx *ctx, size_t bytes, void **d_ptr) {
+    if (!ctx || !d_ptr) return SS_ERR_INVALID;
+    SS_CUDA_CHECK(ctx, cudaMalloc(d_ptr, bytes));
+    return SS_OK;
+}
+
+ss_status ss_free(ss_ctx *ctx, void *d_ptr) {
+    if (!ctx) return SS_ERR_INVALID;
+    SS_CUDA_CHECK(ctx, cudaFree(d_ptr));
+    return SS_OK;
+}
+
+ss_status ss_host_register(ss_ctx *ctx, void *h_ptr, size_t bytes) {
+    if (!ctx || !h_ptr) return SS_ERR_INVALID;
+    SS_CUDA_CHECK(ctx, cudaHostRegister(h_ptr, bytes, cudaHostRegisterDefault));
+    return SS_OK;
+}
+
+ss_status ss_host_unregister(ss_ctx *ctx, void *h_ptr) {
+    if (!ctx || !h_ptr) return SS_ERR_INVALID;
+    SS_CUDA_CHECK(ctx, cudaHostUnregister(h_ptr));
+    return SS_OK;
+}
+
+ss_status ss_memcpy_h2d(ss_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, void *stream) {
+    if (!ctx) return SS_ERR_INVALID;
+    SS_CUDA_CHECK(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, pick_stream(ctx, stream)));
+    return SS_OK;
+}
+
+ss_status ss_memcpy_d2h(ss_ctx *ctx, void *h_dst, const void *d_src, size_t bytes, void *stream) {
+    if (!ctx) return SS_ERR_INVALID;
+    SS_CUDA_CHECK(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, pick_stream(ctx, stream)));
+    return SS_OK;
+}
+
+}  // extern "C"

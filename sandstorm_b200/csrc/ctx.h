@@ -1,0 +1,54 @@
+// Internal context shared by the translation units of libsandstorm_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+#include "../../include/sandstorm_b200.h"
+#include "fp252.cuh"
+
+struct ss_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;            // ctx-owned default stream
+    std::string err;
+    // cached device tables, keyed by (kind, log_n, variant)
+    std::map<std::tuple<int, int, int>, void *> tables;
+    // grow-only scratch (LDE coefficient buffer etc.)
+    void *scratch = nullptr;
+    size_t scratch_bytes = 0;
+    int sm_count = 148;
+};
+
+namespace ss {
+
+inline ss_status fail(ss_ctx *ctx, ss_status code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+#define SS_CUDA_CHECK(ctx, expr)                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return ss::fail(ctx, e_ == cudaErrorMemoryAllocation ? SS_ERR_OOM : SS_ERR_CUDA,       \
+                            "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+inline cudaStream_t pick_stream(ss_ctx *ctx, void *stream) {
+    return stream ? reinterpret_cast<cudaStream_t>(stream) : ctx->stream;
+}
+
+ss_status scratch_reserve(ss_ctx *ctx, size_t bytes, void **out);
+// uploads a host table once and caches it; `fill` computes n elements of 32 bytes
+ss_status cached_table(ss_ctx *ctx, std::tuple<int, int, int> key, size_t n_elems,
+                       void (*fill)(Fp *dst, size_t n, int log_n, int variant), Fp **out);
+
+}  // namespace ss

@@ -1,0 +1,258 @@
+// Host side of the Fp252 NTT / LDE: twiddle + scale tables, pass planning, kernel launches,
+// and the ss_ntt / ss_lde entry points (include/sandstorm_b200.h).
+#include "ctx.h"
+#include "ntt_fp252.cuh"
+
+using namespace ss;
+
+namespace {
+
+enum TableKind : int { T_LOCAL = 1, T_LO = 2, T_HI = 3, T_SCALE_LO = 4, T_SCALE_HI = 5 };
+enum ScaleVariant : int { SV_LDE = 0, SV_COSET_FWD = 1, SV_COSET_INV = 2, SV_NINV = 3 };
+
+// w_n = 3^((p-1)/n), n = 2^log_n; inverse -> w_n^-1.  Canonical Montgomery form.
+Fp root_of_unity(int log_n, bool inverse) {
+    uint32_t e[8] = {0, 0, 0, 0, 0, 0, 0x00000011u, 0x08000000u};   // p - 1
+    for (int s = 0; s < log_n; ++s) {
+        for (int i = 0; i < 8; ++i) {
+            e[i] >>= 1;
+            if (i < 7) e[i] |= e[i + 1] << 31;
+        }
+    }
+    Fp w = fp::pow_limbs(fp::from_u32(3), e, 8);
+    if (inverse) w = fp::inv(w);
+    return fp::canon(w);
+}
+
+// dst[i] = c * h^i
+void geometric(Fp *dst, size_t n, Fp c, const Fp &h) {
+    for (size_t i = 0; i < n; ++i) {
+        dst[i] = fp::canon(c);
+        c = fp::mul(c, h);
+    }
+}
+
+void fill_local(Fp *dst, size_t n, int, int inverse) { geometric(dst, n, fp::one(), root_of_unity(NTT_LOG_TILE, inverse != 0)); }
+void fill_lo(Fp *dst, size_t n, int log_n, int inverse) { geometric(dst, n, fp::one(), root_of_unity(log_n, inverse != 0)); }
+void fill_hi(Fp *dst, size_t n, int log_n, int inverse) {
+    const Fp w = root_of_unity(log_n, inverse != 0);
+    geometric(dst, n, fp::one(), fp::pow_u64(w, 4096));
+}
+
+void scale_params(int log_n, int variant, Fp &c, Fp &h) {
+    Fp ninv = fp::inv(fp::pow_u64(fp::from_u32(2), (uint64_t)log_n));
+    const Fp g = fp::from_u32(3);          // Fp::GENERATOR, the LDE coset offset
+    switch (variant) {
+    case SV_LDE: c = ninv; h = g; break;
+    case SV_COSET_FWD: c = fp::one(); h = g; break;
+    case SV_COSET_INV: c = ninv; h = fp::inv(g); break;
+    default: c = ninv; h = fp::one(); break;
+    }
+}
+void fill_scale_lo(Fp *dst, size_t n, int log_n, int variant) {
+    Fp c, h;
+    scale_params(log_n, variant, c, h);
+    geometric(dst, n, c, h);
+}
+void fill_scale_hi(Fp *dst, size_t n, int log_n, int variant) {
+    Fp c, h;
+    scale_params(log_n, variant, c, h);
+    geometric(dst, n, fp::one(), fp::pow_u64(h, 4096));
+}
+
+std::vector<int> plan_passes(int log_n) {
+    if (log_n <= NTT_LOG_TILE) return {log_n};
+    const int k = (log_n + NTT_LOG_TILE - 1) / NTT_LOG_TILE;
+    std::vector<int> out;
+    for (int i = 0; i < k; ++i) out.push_back(log_n / k + (i < log_n % k ? 1 : 0));
+    return out;
+}
+
+struct NttJob {
+    Fp *dst;
+    const Fp *src;
+    uint64_t dst_stride, src_stride;
+    int n_cols, log_n;
+    bool inverse, dit;
+    int expand_log;            // DIT only: first pass reads src[p >> expand_log]
+    int pre_scale, post_scale; // NttScaleMode
+    int scale_variant;
+    bool canon_out;
+};
+
+template <bool DIT>
+ss_status launch_pass(ss_ctx *ctx, const NttPass &p, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        SS_CUDA_CHECK(ctx, cudaFuncSetAttribute(ntt_pass_kernel<DIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT_SMEM_BYTES));
+        configured = true;
+    }
+    dim3 grid;
+    if (p.log_n < NTT_LOG_TILE) {
+        const int per_tile = 1 << (NTT_LOG_TILE - p.log_n);
+        grid = dim3((p.n_cols + per_tile - 1) / per_tile, 1, 1);
+    } else {
+        grid = dim3(1u << (p.log_n - NTT_LOG_TILE), p.n_cols, 1);
+    }
+    ntt_pass_kernel<DIT><<<grid, NTT_THREADS, NTT_SMEM_BYTES, st>>>(p);
+    SS_CUDA_CHECK(ctx, cudaGetLastError());
+    return SS_OK;
+}
+
+ss_status run_ntt(ss_ctx *ctx, const NttJob &job, cudaStream_t st) {
+    if (job.log_n == 0) {
+        if (job.dst != job.src)
+            for (int c = 0; c < job.n_cols; ++c)
+                SS_CUDA_CHECK(ctx, cudaMemcpyAsync(job.dst + c * job.dst_stride, job.src + c * job.src_stride, sizeof(Fp), cudaMemcpyDeviceToDevice, st));
+        return SS_OK;
+    }
+    const int inv = job.inverse ? 1 : 0;
+    Fp *tw_local, *tw_lo, *tw_hi, *sc_lo = nullptr, *sc_hi = nullptr;
+    ss_status rc;
+    const size_t n = (size_t)1 << job.log_n;
+    if ((rc = cached_table(ctx, {T_LOCAL, NTT_LOG_TILE, inv}, 2048, fill_local, &tw_local))) return rc;
+    if ((rc = cached_table(ctx, {T_LO, job.log_n, inv}, n < 4096 ? n : 4096, fill_lo, &tw_lo))) return rc;
+    if ((rc = cached_table(ctx, {T_HI, job.log_n, inv}, n <= 4096 ? 1 : n / 4096, fill_hi, &tw_hi))) return rc;
+    if (job.pre_scale != SCALE_NONE || job.post_scale != SCALE_NONE) {
+        const bool is_const = job.pre_scale == SCALE_CONST || job.post_scale == SCALE_CONST;
+        if ((rc = cached_table(ctx, {T_SCALE_LO, job.log_n, job.scale_variant}, is_const ? 1 : (n < 4096 ? n : 4096), fill_scale_lo, &sc_lo))) return rc;
+        if (!is_const)
+            if ((rc = cached_table(ctx, {T_SCALE_HI, job.log_n, job.scale_variant}, n <= 4096 ? 1 : n / 4096, fill_scale_hi, &sc_hi))) return rc;
+    }
+    const std::vector<int> passes = plan_passes(job.log_n);
+    const int np = (int)passes.size();
+    int log_b = job.dit ? 0 : job.log_n;
+    for (int i = 0; i < np; ++i) {
+        const int L = job.dit ? passes[np - 1 - i] : passes[i];
+        if (job.dit) log_b += L;
+        NttPass p{};
+        const bool first = i == 0, last = i == np - 1;
+        p.dst = job.dst;
+        p.src = first ? job.src : job.dst;
+        p.dst_col_stride = job.dst_stride;
+        p.src_col_stride = first ? job.src_stride : job.dst_stride;
+        p.n_cols = job.n_cols;
+        p.log_n = job.log_n;
+        p.log_block = log_b;
+        p.L = L;
+        p.contiguous = (log_b == L) ? 1 : 0;
+        p.expand_log = first ? job.expand_log : 0;
+        p.tw_local = tw_local;
+        p.tw_lo = tw_lo;
+        p.tw_hi = tw_hi;
+        p.pre_scale = first ? job.pre_scale : SCALE_NONE;
+        p.post_scale = last ? job.post_scale : SCALE_NONE;
+        p.scale_lo = sc_lo;
+        p.scale_hi = sc_hi;
+        p.canon_out = (last && job.canon_out) ? 1 : 0;
+        rc = job.dit ? launch_pass<true>(ctx, p, st) : launch_pass<false>(ctx, p, st);
+        if (rc) return rc;
+        if (!job.dit) log_b -= L;
+    }
+    return SS_OK;
+}
+
+// in-place bit-reversal permutation of every column
+__global__ void bitrev_permute_kernel(Fp *cols, unsigned long long stride, int log_n) {
+    const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (i >> log_n) return;
+    const unsigned long long j = __brevll(i) >> (64 - log_n);
+    if (i < j) {
+        uint4 *a = reinterpret_cast<uint4 *>(cols + blockIdx.y * stride + i);
+        uint4 *b = reinterpret_cast<uint4 *>(cols + blockIdx.y * stride + j);
+        const uint4 a0 = a[0], a1 = a[1], b0 = b[0], b1 = b[1];
+        a[0] = b0; a[1] = b1; b[0] = a0; b[1] = a1;
+    }
+}
+
+ss_status bitrev_permute(ss_ctx *ctx, Fp *cols, uint64_t stride, int n_cols, int log_n, cudaStream_t st) {
+    if (log_n < 2) return SS_OK;
+    const unsigned long long n = 1ull << log_n;
+    dim3 grid((unsigned)((n + 255) / 256), n_cols, 1);
+    bitrev_permute_kernel<<<grid, 256, 0, st>>>(cols, stride, log_n);
+    SS_CUDA_CHECK(ctx, cudaGetLastError());
+    return SS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+ss_status ss_ntt(ss_ctx *ctx, ss_field field, void *d_cols, uint64_t col_stride, int n_cols, int log_n,
+                 int inverse, int coset, ss_order in_order, ss_order out_order, void *stream) {
+    if (!ctx) return SS_ERR_INVALID;
+    if (field != SS_FIELD_FP252) return fail(ctx, SS_ERR_UNSUPPORTED, "ss_ntt: field %d not built", (int)field);
+    if (!d_cols || n_cols < 0 || log_n < 0 || log_n > 40 || col_stride < (1ull << log_n))
+        return fail(ctx, SS_ERR_INVALID, "ss_ntt: bad arguments (n_cols=%d log_n=%d stride=%llu)", n_cols, log_n, (unsigned long long)col_stride);
+    if (n_cols == 0) return SS_OK;
+    SS_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = pick_stream(ctx, stream);
+    NttJob job{};
+    job.dst = static_cast<Fp *>(d_cols);
+    job.src = job.dst;
+    job.dst_stride = job.src_stride = col_stride;
+    job.n_cols = n_cols;
+    job.log_n = log_n;
+    job.inverse = inverse != 0;
+    job.dit = in_order == SS_ORDER_BITREV;          // DIF eats natural order, DIT eats bit-reversed
+    job.canon_out = true;
+    // position -> coefficient/evaluation index is brev(pos) on the bit-reversed side of the transform
+    if (!inverse) {
+        if (coset) { job.pre_scale = job.dit ? SCALE_TABLE_BREV : SCALE_TABLE_NAT; job.scale_variant = SV_COSET_FWD; }
+    } else {
+        if (coset) { job.post_scale = job.dit ? SCALE_TABLE_NAT : SCALE_TABLE_BREV; job.scale_variant = SV_COSET_INV; }
+        else       { job.post_scale = SCALE_CONST; job.scale_variant = SV_NINV; }
+    }
+    ss_status rc = run_ntt(ctx, job, st);
+    if (rc) return rc;
+    const ss_order produced = job.dit ? SS_ORDER_NATURAL : SS_ORDER_BITREV;
+    if (produced != out_order) return bitrev_permute(ctx, job.dst, col_stride, n_cols, log_n, st);
+    return SS_OK;
+}
+
+ss_status ss_lde(ss_ctx *ctx, ss_field field, const void *d_trace, uint64_t trace_stride, int n_cols,
+                 int log_n, int log_blowup, void *d_lde, uint64_t lde_stride, void *d_coeffs,
+                 uint64_t coeff_stride, ss_order out_order, void *stream) {
+    if (!ctx) return SS_ERR_INVALID;
+    if (field != SS_FIELD_FP252) return fail(ctx, SS_ERR_UNSUPPORTED, "ss_lde: field %d not built", (int)field);
+    if (!d_trace || !d_lde || n_cols < 0 || log_n < 0 || log_blowup < 0 || log_n + log_blowup > 40 ||
+        trace_stride < (1ull << log_n) || lde_stride < (1ull << (log_n + log_blowup)) ||
+        (d_coeffs && coeff_stride < (1ull << log_n)))
+        return fail(ctx, SS_ERR_INVALID, "ss_lde: bad arguments");
+    if (n_cols == 0) return SS_OK;
+    SS_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = pick_stream(ctx, stream);
+    const size_t n = (size_t)1 << log_n;
+    Fp *coeffs = static_cast<Fp *>(d_coeffs);
+    uint64_t cstride = coeff_stride;
+    if (!coeffs) {
+        void *scratch;
+        ss_status rc = scratch_reserve(ctx, (size_t)n_cols * n * sizeof(Fp), &scratch);
+        if (rc) return rc;
+        coeffs = static_cast<Fp *>(scratch);
+        cstride = n;
+    }
+    // 1) inverse DIF: evaluations (natural) -> coefficients (bit-reversed) * n^-1 * 3^k
+    NttJob inv{};
+    inv.dst = coeffs; inv.src = static_cast<const Fp *>(d_trace);
+    inv.dst_stride = cstride; inv.src_stride = trace_stride;
+    inv.n_cols = n_cols; inv.log_n = log_n; inv.inverse = true; inv.dit = false;
+    inv.post_scale = SCALE_TABLE_BREV; inv.scale_variant = SV_LDE; inv.canon_out = true;
+    ss_status rc = run_ntt(ctx, inv, st);
+    if (rc) return rc;
+    // 2) forward DIT of size N; bit-reversed zero padding = coefficient p sits at position p << log_blowup
+    NttJob fwd{};
+    fwd.dst = static_cast<Fp *>(d_lde); fwd.src = coeffs;
+    fwd.dst_stride = lde_stride; fwd.src_stride = cstride;
+    fwd.n_cols = n_cols; fwd.log_n = log_n + log_blowup; fwd.inverse = false; fwd.dit = true;
+    fwd.expand_log = log_blowup; fwd.canon_out = true;
+    if (log_blowup == 0 && log_n == 0) {
+        // degenerate: single element, DIT job with log_n 0 copies src -> dst
+    }
+    rc = run_ntt(ctx, fwd, st);
+    if (rc) return rc;
+    if (out_order == SS_ORDER_BITREV) return bitrev_permute(ctx, fwd.dst, lde_stride, n_cols, log_n + log_blowup, st);
+    return SS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,86 @@
+"""Device-resident column-major matrix: the mirror of ``ministark::Matrix<Fp>``
+(constructed at reference layouts/src/recursive/trace.rs:652-660; read through
+num_rows / num_cols / read_row at crypto/src/merkle/utils.rs:20,37,40)."""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .context import Context, default_context
+
+
+def _stream_ptr() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Matrix:
+    """``data``: torch.int64 CUDA tensor of shape (n_cols, n_rows, 4): Montgomery limbs, column-major."""
+
+    def __init__(self, data: torch.Tensor, ctx: Context | None = None):
+        if data.dtype != torch.int64 or data.dim() != 3 or data.shape[2] != 4 or not data.is_cuda:
+            raise ValueError("Matrix expects a CUDA int64 tensor of shape (n_cols, n_rows, 4)")
+        if not data.is_contiguous():
+            data = data.contiguous()
+        n = data.shape[1]
+        if n & (n - 1):
+            raise ValueError("number of rows must be a power of two")
+        self.data = data
+        self.ctx = ctx or default_context(data.device.index)
+
+    # ---- construction / export -------------------------------------------------------------
+    @classmethod
+    def from_numpy(cls, cols: np.ndarray, device: str = "cuda", ctx: Context | None = None) -> "Matrix":
+        a = np.ascontiguousarray(cols, dtype=np.uint64)
+        return cls(torch.from_numpy(a.view(np.int64)).to(device), ctx)
+
+    def numpy(self) -> np.ndarray:
+        return self.data.cpu().numpy().view(np.uint64)
+
+    @property
+    def num_cols(self) -> int:
+        return self.data.shape[0]
+
+    @property
+    def num_rows(self) -> int:
+        return self.data.shape[1]
+
+    @property
+    def log_rows(self) -> int:
+        return self.num_rows.bit_length() - 1
+
+    def clone(self) -> "Matrix":
+        return Matrix(self.data.clone(), self.ctx)
+
+    # ---- ministark Matrix::{interpolate, evaluate} --------------------------------------------
+    def ntt_(self, inverse: bool = False, coset: bool = False, in_order: int = _lib.ORDER_NATURAL,
+             out_order: int = _lib.ORDER_NATURAL) -> "Matrix":
+        c = self.ctx
+        c.check(c.lib.ss_ntt(c.handle, _lib.FIELD_FP252, ctypes.c_void_p(self.data.data_ptr()), self.num_rows,
+                             self.num_cols, self.log_rows, int(inverse), int(coset), in_order, out_order, _stream_ptr()))
+        return self
+
+    def interpolate(self) -> "Matrix":
+        """Matrix::interpolate(trace_domain): evaluations on <w_n> -> coefficients (natural order)."""
+        return self.clone().ntt_(inverse=True)
+
+    def evaluate(self, log_blowup: int = 0, coset: bool = True) -> "Matrix":
+        """Matrix::evaluate(domain): coefficients -> evaluations on (3 if coset)*<w_N>, N = n << log_blowup."""
+        n_cols, n = self.num_cols, self.num_rows
+        out = torch.zeros((n_cols, n << log_blowup, 4), dtype=torch.int64, device=self.data.device)
+        out[:, :n] = self.data
+        return Matrix(out, self.ctx).ntt_(inverse=False, coset=coset)
+
+    def lde(self, log_blowup: int, keep_coeffs: bool = False, out_order: int = _lib.ORDER_NATURAL):
+        """interpolate + evaluate on the LDE coset, fused (ss_lde).  Returns lde or (lde, coeffs)."""
+        c = self.ctx
+        n_cols, n = self.num_cols, self.num_rows
+        out = torch.empty((n_cols, n << log_blowup, 4), dtype=torch.int64, device=self.data.device)
+        coeffs = torch.empty_like(self.data) if keep_coeffs else None
+        c.check(c.lib.ss_lde(c.handle, _lib.FIELD_FP252, ctypes.c_void_p(self.data.data_ptr()), n, n_cols, self.log_rows,
+                             log_blowup, ctypes.c_void_p(out.data_ptr()), n << log_blowup,
+                             ctypes.c_void_p(coeffs.data_ptr()) if keep_coeffs else None, n, out_order, _stream_ptr()))
+        lde = Matrix(out, c)
+        return (lde, Matrix(coeffs, c)) if keep_coeffs else lde
