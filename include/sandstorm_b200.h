@@ -16,7 +16,7 @@
  *   - matrices are column-major, one contiguous column of 2^log_rows elements every `col_stride`
  *     elements: the layout of ministark::Matrix (Vec<GpuVec<F>>), SURVEY.md §8 a1.
  *   - d_* pointers are device memory of the ctx's GPU, h_* pointers are host memory.
- *   - `stream` is a cudaStream_t passed as void* (NULL = the ctx's own stream).  Calls are
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the CUDA default stream).  Calls are
  *     asynchronous on that stream unless stated; one ss_ctx per (thread, device).
  */
 #ifndef SANDSTORM_B200_H

@@ -8,7 +8,7 @@ namespace ss {
 ss_status scratch_reserve(ss_ctx *ctx, size_t bytes, void **out) {
     if (bytes > ctx->scratch_bytes) {
         if (ctx->scratch) {
-            SS_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+            SS_CUDA_CHECK(ctx, cudaDeviceSynchronize());
             SS_CUDA_CHECK(ctx, cudaFree(ctx->scratch));
             ctx->scratch = nullptr;
             ctx->scratch_bytes = 0;
@@ -66,7 +66,7 @@ ss_status ss_create(int device, ss_ctx **out) {
 void ss_destroy(ss_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    cudaDeviceSynchronize();
     for (auto &kv : ctx->tables) cudaFree(kv.second);
     if (ctx->scratch) cudaFree(ctx->scratch);
     cudaStreamDestroy(ctx->stream);
@@ -77,7 +77,7 @@ const char *ss_last_error(const ss_ctx *ctx) { return ctx ? ctx->err.c_str() : "
 
 ss_status ss_sync(ss_ctx *ctx) {
     if (!ctx) return SS_ERR_INVALID;
-    SS_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    SS_CUDA_CHECK(ctx, cudaDeviceSynchronize());
     return SS_OK;
 }
 

@@ -42,9 +42,8 @@ inline ss_status fail(ss_ctx *ctx, ss_status code, const char *fmt, ...) {
                             "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-inline cudaStream_t pick_stream(ss_ctx *ctx, void *stream) {
-    return stream ? reinterpret_cast<cudaStream_t>(stream) : ctx->stream;
-}
+// `stream` follows the CUDA convention: a cudaStream_t passed as void*, NULL = the default stream.
+inline cudaStream_t pick_stream(ss_ctx *, void *stream) { return reinterpret_cast<cudaStream_t>(stream); }
 
 ss_status scratch_reserve(ss_ctx *ctx, size_t bytes, void **out);
 // uploads a host table once and caches it; `fill` computes n elements of 32 bytes

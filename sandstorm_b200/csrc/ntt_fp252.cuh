@@ -87,11 +87,16 @@ __device__ __forceinline__ void st_stream(Fp *p, const Fp &v) {
     __stcs(q + 1, make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]));
 }
 
+// lo[i] = c * h^i (i < 4096), hi[i] = h^(4096 i):  c * h^k
 __device__ __forceinline__ Fp two_level(const Fp *lo, const Fp *hi, unsigned long long k) {
-    if ((k & 4095ull) == 0) return ldg_fp(hi + (k >> 12));
     Fp v = ldg_fp(lo + (k & 4095ull));
     if (k >> 12) v = fp::mul(v, ldg_fp(hi + (k >> 12)));
     return v;
+}
+// twiddle tables have c = 1, so a multiple of 4096 needs no multiplication
+__device__ __forceinline__ Fp two_level_tw(const Fp *lo, const Fp *hi, unsigned long long k) {
+    if ((k & 4095ull) == 0) return ldg_fp(hi + (k >> 12));
+    return two_level(lo, hi, k);
 }
 
 __device__ __forceinline__ Fp apply_scale(const Fp &x, int mode, const Fp *lo, const Fp *hi,
@@ -168,11 +173,12 @@ __global__ void __launch_bounds__(NTT_THREADS, 1) ntt_pass_kernel(const NttPass 
         const unsigned int l = (unsigned int)(tau >> (NTT_LOG_TILE - L));
         const unsigned long long r = (unsigned long long)(__brev(l) >> (32 - L));
         const unsigned long long e = (lo * r) << (P.log_n - lb);
-        return nttk::two_level(P.tw_lo, P.tw_hi, e);
+        return nttk::two_level_tw(P.tw_lo, P.tw_hi, e);
     };
 
     // ---------------------------------------------------------------- load
-#pragma unroll 2
+    // fully unrolled: 16 independent LDG.128 in flight per thread before the first STS
+#pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int tau = t + NTT_THREADS * i;
         int col; unsigned long long pos;
