@@ -49,3 +49,50 @@ void hc_fp_from_u32(uint32_t v, uint32_t *out) {
 }
 
 }  // extern "C"
+
+// ---- hash cores and Pedersen (host build of the device code) ----
+#include "hashes.cuh"
+#include "pedersen.cuh"
+#include <vector>
+
+extern "C" {
+
+// msg: n_bytes (multiple of 8) -> Keccak-256 digest
+void hc_keccak256(const uint8_t *msg, int n_bytes, uint8_t *out) {
+    const uint64_t *l = reinterpret_cast<const uint64_t *>(msg);
+    auto lane = [&](int g) -> uint64_t { uint64_t v; std::memcpy(&v, msg + 8 * g, 8); (void)l; return v; };
+    uint64_t d[4];
+    hash::keccak256_lanes(lane, n_bytes / 8, d);
+    std::memcpy(out, d, 32);
+}
+void hc_blake2s256(const uint8_t *msg, int n_bytes, uint8_t *out) {
+    auto word = [&](int g) -> uint32_t { uint32_t v; std::memcpy(&v, msg + 4 * g, 4); return v; };
+    uint32_t h[8];
+    hash::blake2s256_words(word, n_bytes / 4, h);
+    std::memcpy(out, h, 32);
+}
+void hc_sha256(const uint8_t *msg, int n_bytes, uint8_t *out) {
+    auto word = [&](int g) -> uint32_t { return ((uint32_t)msg[4 * g] << 24) | ((uint32_t)msg[4 * g + 1] << 16) | ((uint32_t)msg[4 * g + 2] << 8) | msg[4 * g + 3]; };
+    uint32_t h[8];
+    hash::sha256_words(word, n_bytes / 4, h);
+    for (int i = 0; i < 8; ++i) { out[4 * i] = h[i] >> 24; out[4 * i + 1] = h[i] >> 16; out[4 * i + 2] = h[i] >> 8; out[4 * i + 3] = h[i]; }
+}
+void hc_pedersen(const uint32_t *a, const uint32_t *b, uint32_t *out) {
+    static std::vector<Fp> table;
+    if (table.empty()) {
+        table.resize(2 * (size_t)(ec::PED_TABLE_POINTS + 1));
+        ec::fill_pedersen_table(table.data(), table.size(), 0, 0);
+    }
+    const AffinePt *pts = reinterpret_cast<const AffinePt *>(table.data());
+    Fp x, y;
+    std::memcpy(x.l, a, 32);
+    std::memcpy(y.l, b, 32);
+    const Fp h = ec::pedersen_hash(x, y, pts[ec::PED_TABLE_POINTS], [&](int i) { return pts[i]; });
+    std::memcpy(out, h.l, 32);
+}
+void hc_inv_chain(const uint32_t *a, uint32_t *out) {
+    Fp x; std::memcpy(x.l, a, 32);
+    Fp r = fp::canon(ec::inv_chain(x)); std::memcpy(out, r.l, 32);
+}
+
+}  // extern "C"
