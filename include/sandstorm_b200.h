@@ -65,6 +65,8 @@ ss_status ss_create(int device, ss_ctx **out);
 void ss_destroy(ss_ctx *ctx);
 const char *ss_last_error(const ss_ctx *ctx);
 ss_status ss_sync(ss_ctx *ctx);
+/* number of CUDA kernels this ctx has launched so far (bench.py reports the per-step delta) */
+uint64_t ss_kernel_launches(const ss_ctx *ctx);
 /* thin wrappers so that a host without the CUDA runtime (Rust) can own device buffers;
  * replaces ministark_gpu's GpuAllocator / GpuVec role (layouts/src/recursive/trace.rs:55-56,115) */
 ss_status ss_malloc(ss_ctx *ctx, size_t bytes, void **d_ptr);
@@ -111,6 +113,9 @@ ss_status ss_merkle_leaves(ss_ctx *ctx, const ss_tree *tree, const uint64_t *h_i
 /* MerkleTree::prove(indices): sibling path of each index, leaf level first (log_rows * 32 bytes each) */
 ss_status ss_merkle_open(ss_ctx *ctx, const ss_tree *tree, const uint64_t *h_indices, size_t n,
                          uint8_t *h_paths /* n * log_rows * 32 */);
+/* Root of a row-sharded commitment: 2^log_count sub-tree roots (one per GPU row range, in row
+ * order) -> root of the whole tree.  Byte-hash kinds only.  Synchronises. */
+ss_status ss_merkle_combine(ss_ctx *ctx, ss_tree_kind kind, const uint8_t *h_subroots, int log_count, uint8_t root[32]);
 int ss_tree_log_rows(const ss_tree *tree);
 void ss_tree_free(ss_tree *tree);
 /* batch Pedersen hash (builtins/src/pedersen/mod.rs:31-36), Montgomery limbs in and out */

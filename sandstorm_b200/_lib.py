@@ -24,6 +24,7 @@ SIGNATURES = {
     "ss_destroy": (None, [c_void_p]),
     "ss_last_error": (c_char_p, [c_void_p]),
     "ss_sync": (c_int, [c_void_p]),
+    "ss_kernel_launches": (c_uint64, [c_void_p]),
     "ss_malloc": (c_int, [c_void_p, c_size_t, POINTER(c_void_p)]),
     "ss_free": (c_int, [c_void_p, c_void_p]),
     "ss_host_register": (c_int, [c_void_p, c_void_p, c_size_t]),
@@ -37,6 +38,7 @@ SIGNATURES = {
     "ss_merkle_nodes": (c_int, [c_void_p, c_void_p, POINTER(c_uint64), c_size_t, POINTER(c_uint8)]),
     "ss_merkle_leaves": (c_int, [c_void_p, c_void_p, POINTER(c_uint64), c_size_t, POINTER(c_uint8)]),
     "ss_merkle_open": (c_int, [c_void_p, c_void_p, POINTER(c_uint64), c_size_t, POINTER(c_uint8)]),
+    "ss_merkle_combine": (c_int, [c_void_p, c_int, POINTER(c_uint8), c_int, POINTER(c_uint8)]),
     "ss_tree_log_rows": (c_int, [c_void_p]),
     "ss_tree_free": (None, [c_void_p]),
     "ss_pedersen_hash": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -81,6 +81,8 @@ ss_status ss_sync(ss_ctx *ctx) {
     return SS_OK;
 }
 
+uint64_t ss_kernel_launches(const ss_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
 ss_status ss_malloc(ss_ctx *ctx, size_t bytes, void **d_ptr) {
     if (!ctx || !d_ptr) return SS_ERR_INVALID;
     SS_CUDA_CHECK(ctx, cudaMalloc(d_ptr, bytes));

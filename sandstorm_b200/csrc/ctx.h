@@ -20,6 +20,7 @@ struct ss_ctx {
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
     int sm_count = 148;
+    unsigned long long launches = 0;          // kernels launched by this ctx (ss_kernel_launches)
 };
 
 namespace ss {

@@ -286,13 +286,16 @@ ss_status ss_merkle_build(ss_ctx *ctx, ss_tree_kind kind, int n_friendly, const 
     ss_status rc = SS_OK;
     if (n_cols == 1) {
         copy_column_kernel<<<grid_for(n, 256), 256, 0, st>>>(cols, log_rows, bitrev, t->d_leaves);
+        ctx->launches++;
         const unsigned long long cnt = n / 2;
         uint8_t *lvl = t->d_nodes + 32ull * cnt;
         if (kind == SS_TREE_FRIENDLY) {
             pedersen_node_kernel<<<grid_for(cnt, 128), 128, 0, st>>>(t->d_leaves, cnt, 2, tab, lvl);
+            ctx->launches++;
         } else {
             rc = by_byte_hash(bh, [&](auto BH) {
                 leafpair_hash_kernel<decltype(BH)::value><<<grid_for(cnt, 128), 128, 0, st>>>(reinterpret_cast<const Fp *>(t->d_leaves), cnt, mask, lvl);
+                ctx->launches++;
                 return SS_OK;
             });
         }
@@ -302,9 +305,11 @@ ss_status ss_merkle_build(ss_ctx *ctx, ss_tree_kind kind, int n_friendly, const 
             uint8_t *dst = t->d_nodes + 32ull * c;
             if (kind == SS_TREE_FRIENDLY) {
                 pedersen_node_kernel<<<grid_for(c, 128), 128, 0, st>>>(children, c, 0, tab, dst);
+                ctx->launches++;
             } else {
                 by_byte_hash(bh, [&](auto BH) {
                     node_hash_kernel<decltype(BH)::value><<<grid_for(c, 128), 128, 0, st>>>(children, c, mask, dst);
+                    ctx->launches++;
                     return SS_OK;
                 });
             }
@@ -312,6 +317,7 @@ ss_status ss_merkle_build(ss_ctx *ctx, ss_tree_kind kind, int n_friendly, const 
     } else {
         by_byte_hash(bh, [&](auto BH) {
             leaf_hash_kernel<decltype(BH)::value><<<grid_for(n, 128), 128, 0, st>>>(cols, col_stride, n_cols, log_rows, bitrev, mask, t->d_leaves);
+            ctx->launches++;
             return SS_OK;
         });
         const int transition = kind == SS_TREE_FRIENDLY ? n_friendly : 0;
@@ -322,11 +328,13 @@ ss_status ss_merkle_build(ss_ctx *ctx, ss_tree_kind kind, int n_friendly, const 
             if (d >= transition) {
                 by_byte_hash(bh, [&](auto BH) {
                     node_hash_kernel<decltype(BH)::value><<<grid_for(c, 128), 128, 0, st>>>(children, c, mask, dst);
+                    ctx->launches++;
                     return SS_OK;
                 });
             } else {
                 const bool child_high = (d + 1 < transition) && (d != height - 1);
                 pedersen_node_kernel<<<grid_for(c, 128), 128, 0, st>>>(children, c, child_high ? 0 : 1, tab, dst);
+                ctx->launches++;
             }
         }
     }
@@ -371,6 +379,7 @@ static ss_status gather_virtual(ss_ctx *ctx, const ss_tree *tree, const std::vec
     if (e != cudaSuccess) { cudaFree(d_idx); return fail(ctx, SS_ERR_OOM, "gather: out of memory"); }
     cudaMemcpy(d_idx, v.data(), v.size() * 8, cudaMemcpyHostToDevice);
     gather32_kernel<<<grid_for(v.size(), 128), 128>>>(tree->d_leaves, tree->d_nodes, 1ull << tree->log_rows, d_idx, v.size(), d_out);
+    tree->ctx->launches++;
     e = cudaMemcpy(h_out, d_out, v.size() * 32, cudaMemcpyDeviceToHost);
     cudaFree(d_idx); cudaFree(d_out);
     if (e != cudaSuccess) return fail(ctx, SS_ERR_CUDA, "gather: %s", cudaGetErrorString(e));
@@ -413,6 +422,32 @@ ss_status ss_merkle_open(ss_ctx *ctx, const ss_tree *tree, const uint64_t *h_ind
     return gather_virtual(ctx, tree, v, h_paths);
 }
 
+// Top of a row-sharded tree: `count` = 2^log_count sub-tree roots (storage form, byte-hash kinds) ->
+// root of the tree whose leaves they are.  Used when each GPU commits a row range.
+ss_status ss_merkle_combine(ss_ctx *ctx, ss_tree_kind kind, const uint8_t *h_subroots, int log_count, uint8_t root[32]) {
+    if (!ctx || !h_subroots || !root || log_count < 0 || log_count > 16) return SS_ERR_INVALID;
+    if (kind == SS_TREE_FRIENDLY) return fail(ctx, SS_ERR_UNSUPPORTED, "ss_merkle_combine: algebraic top layers are not sharded");
+    const unsigned long long count = 1ull << log_count;
+    if (log_count == 0) { for (int i = 0; i < 32; ++i) root[i] = h_subroots[i]; return SS_OK; }
+    int bh, mask;
+    byte_hash_of(kind, bh, mask);
+    uint8_t *d = nullptr;                       // nodes[count .. 2count) = sub-roots, nodes[1] = root
+    SS_CUDA_CHECK(ctx, cudaMalloc(&d, 2 * count * 32));
+    cudaMemcpy(d + 32 * count, h_subroots, count * 32, cudaMemcpyHostToDevice);
+    for (int lvl = log_count - 1; lvl >= 0; --lvl) {
+        const unsigned long long c = 1ull << lvl;
+        by_byte_hash(bh, [&](auto BH) {
+            node_hash_kernel<decltype(BH)::value><<<grid_for(c, 128), 128>>>(d + 64ull * c, c, mask, d + 32ull * c);
+            ctx->launches++;
+            return SS_OK;
+        });
+    }
+    cudaError_t e = cudaMemcpy(root, d + 32, 32, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(ctx, SS_ERR_CUDA, "ss_merkle_combine: %s", cudaGetErrorString(e));
+    return SS_OK;
+}
+
 int ss_tree_log_rows(const ss_tree *tree) { return tree ? tree->log_rows : -1; }
 
 void ss_tree_free(ss_tree *tree) {
@@ -430,6 +465,7 @@ ss_status ss_pedersen_hash(ss_ctx *ctx, const void *d_a, const void *d_b, void *
     ss_status rc = pedersen_table(ctx, &tab);
     if (rc) return rc;
     pedersen_batch_kernel<<<grid_for(n, 128), 128, 0, pick_stream(ctx, stream)>>>(static_cast<const Fp *>(d_a), static_cast<const Fp *>(d_b), static_cast<Fp *>(d_out), n, tab);
+    ctx->launches++;
     SS_CUDA_CHECK(ctx, cudaGetLastError());
     return SS_OK;
 }
@@ -445,6 +481,7 @@ ss_status ss_rows_gather(ss_ctx *ctx, const void *d_cols, uint64_t col_stride, i
     if (e != cudaSuccess) { cudaFree(d_idx); return fail(ctx, SS_ERR_OOM, "ss_rows_gather: out of memory"); }
     cudaMemcpy(d_idx, h_indices, n * 8, cudaMemcpyHostToDevice);
     rows_gather_kernel<<<grid_for(n * n_cols, 128), 128>>>(static_cast<const Fp *>(d_cols), col_stride, n_cols, d_idx, n, d_out);
+    ctx->launches++;
     e = cudaMemcpy(h_rows, d_out, n * n_cols * sizeof(Fp), cudaMemcpyDeviceToHost);
     cudaFree(d_idx); cudaFree(d_out);
     if (e != cudaSuccess) return fail(ctx, SS_ERR_CUDA, "ss_rows_gather: %s", cudaGetErrorString(e));

@@ -95,6 +95,7 @@ ss_status launch_pass(ss_ctx *ctx, const NttPass &p, cudaStream_t st) {
         grid = dim3(1u << (p.log_n - NTT_LOG_TILE), p.n_cols, 1);
     }
     ntt_pass_kernel<DIT><<<grid, NTT_THREADS, NTT_SMEM_BYTES, st>>>(p);
+    ctx->launches++;
     SS_CUDA_CHECK(ctx, cudaGetLastError());
     return SS_OK;
 }
@@ -170,6 +171,7 @@ ss_status bitrev_permute(ss_ctx *ctx, Fp *cols, uint64_t stride, int n_cols, int
     const unsigned long long n = 1ull << log_n;
     dim3 grid((unsigned)((n + 255) / 256), n_cols, 1);
     bitrev_permute_kernel<<<grid, 256, 0, st>>>(cols, stride, log_n);
+    ctx->launches++;
     SS_CUDA_CHECK(ctx, cudaGetLastError());
     return SS_OK;
 }

@@ -11,6 +11,7 @@ ss_status ss_merkle_root(ss_ctx *ctx, const ss_tree *, uint8_t *) { return fail(
 ss_status ss_merkle_nodes(ss_ctx *ctx, const ss_tree *, const uint64_t *, size_t, uint8_t *) { return fail(ctx, SS_ERR_UNSUPPORTED, "ss_merkle_nodes: not built"); }
 ss_status ss_merkle_leaves(ss_ctx *ctx, const ss_tree *, const uint64_t *, size_t, uint8_t *) { return fail(ctx, SS_ERR_UNSUPPORTED, "ss_merkle_leaves: not built"); }
 ss_status ss_merkle_open(ss_ctx *ctx, const ss_tree *, const uint64_t *, size_t, uint8_t *) { return fail(ctx, SS_ERR_UNSUPPORTED, "ss_merkle_open: not built"); }
+ss_status ss_merkle_combine(ss_ctx *ctx, ss_tree_kind, const uint8_t *, int, uint8_t *) { return fail(ctx, SS_ERR_UNSUPPORTED, "ss_merkle_combine: not built"); }
 int ss_tree_log_rows(const ss_tree *) { return -1; }
 void ss_tree_free(ss_tree *) {}
 ss_status ss_pedersen_hash(ss_ctx *ctx, const void *, const void *, void *, size_t, void *) { return fail(ctx, SS_ERR_UNSUPPORTED, "ss_pedersen_hash: not built"); }
