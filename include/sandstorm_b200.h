@@ -125,14 +125,19 @@ ss_status ss_rows_gather(ss_ctx *ctx, const void *d_cols, uint64_t col_stride, i
                          const uint64_t *h_indices, size_t n, void *h_rows);
 
 /* ------------------------------------------------------------------ FRI / DEEP (§8 a14, a15) */
-/* one radix-2^log_fold FRI fold of evaluations on offset*<w_N> (natural order) with challenge alpha:
- * out[i] = sum_j alpha^j * f_j(x_i^(2^log_fold)),  out has N >> log_fold elements on the folded coset. */
+/* One FRI fold by F = 2^log_fold (1..4) of evaluations on h*<w_N>, natural order (ministark
+ * FriProver::build_layers / apply_drp, fold factor from cli/src/main.rs:57-58):
+ *   f(x) = sum_{j<F} x^j F_j(x^F)   ->   out[i] = sum_j alpha^j F_j(x_i^F),   i < N/F.
+ * flags bit 0: multiply by F (StarkWare's binary folds with alpha, alpha^2, alpha^4 and no 1/2).
+ * The layer's commitment is ss_merkle_build(d_evals, col_stride = N/F, n_cols = F, log_rows = log_n - log_fold):
+ * row i of the reference's FRI layer matrix is (e[i], e[i + N/F], ...), i.e. the buffer itself. */
 ss_status ss_fri_fold(ss_ctx *ctx, ss_field field, const void *d_evals, int log_n, int log_fold,
-                      const void *h_alpha, const void *h_domain_offset, void *d_out, void *stream);
-/* evaluate polynomials (coefficients as written by ss_lde: coset-scaled, bit-reversed) at points:
- * h_out[i*n_cols + j] = poly_j(z_i)      (OOD evaluations).  Synchronises. */
-ss_status ss_poly_eval(ss_ctx *ctx, ss_field field, const void *d_coeffs, uint64_t coeff_stride, int n_cols,
-                       int log_n, const void *h_points, size_t n_points, void *h_out);
+                      const void *h_alpha, const void *h_domain_offset, int flags, void *d_out, void *stream);
+/* Out-of-domain evaluations (trace / composition polynomials at z * g^k): for e < n_evals,
+ * h_out[e] = poly_{h_cols[e]}(h_points[e]), polynomials given by the coefficient matrix ss_lde writes
+ * (coset-scaled, bit-reversed).  Synchronises. */
+ss_status ss_poly_eval(ss_ctx *ctx, ss_field field, const void *d_coeffs, uint64_t coeff_stride, int log_n,
+                       const int32_t *h_cols, const void *h_points, size_t n_evals, void *h_out);
 
 /* ------------------------------------------------------------------ constraint evaluation (§8 a4-a7)
  * Evaluates a compiled composition-constraint program (the Expr DAG of

@@ -1,0 +1,250 @@
+// FRI layer folding and out-of-domain polynomial evaluation.
+//
+// ss_fri_fold: one fold by F = 2^log_fold of evaluations on the coset h*<w_N> (natural order):
+//     f(x) = sum_{j<F} x^j F_j(x^F)      ->      out[i] = sum_j alpha^j F_j(y_i),  y_i = x_i^F
+// The F evaluations f(x_i * w_F^k), k < F, sit at indices i + k*N/F (the rows of the reference's FRI
+// layer matrix, which is therefore the input buffer itself viewed column-major with stride N/F: the
+// layer commit is ss_merkle_build(d_evals, col_stride = N/F, n_cols = F) with no data movement).
+// Per output: size-F inverse DFT in registers, then Horner in alpha / x_i.  flags bit 0 multiplies by F,
+// which is StarkWare's convention of three binary folds with alpha, alpha^2, alpha^4 and no 1/2 factor
+// (ministark's FriProver is not vendored: convention unpinned).
+//
+// ss_poly_eval: P(z) for polynomials stored as ss_lde writes them (coefficient k scaled by 3^k, at
+// position brev(k)):  P(z) = sum_pos a[pos] * w^brev(pos), w = z/3, evaluated by log n levels of
+// adjacent-pair folds  b[m] = a[2m] + w^(n/2) a[2m+1],  c[m] = b[2m] + w^(n/4) b[2m+1], ...
+#include "ctx.h"
+#include "fp252.cuh"
+
+using namespace ss;
+
+namespace {
+
+__device__ __forceinline__ Fp ld_fp(const Fp *p) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    const uint4 a = __ldg(q), b = __ldg(q + 1);
+    Fp v;
+    v.l[0] = a.x; v.l[1] = a.y; v.l[2] = a.z; v.l[3] = a.w; v.l[4] = b.x; v.l[5] = b.y; v.l[6] = b.z; v.l[7] = b.w;
+    return v;
+}
+__device__ __forceinline__ void st_fp(Fp *p, const Fp &v) {
+    uint4 *q = reinterpret_cast<uint4 *>(p);
+    q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+
+struct FoldParams {
+    Fp winv[8];          // w_F^-j, j < F/2  (inverse DFT twiddles)
+    Fp alpha_hinv;       // alpha / h
+    Fp scale;            // 1/F, or 1 when the StarkWare (x F) convention is requested
+    const Fp *xinv_lo;   // w_N^-i,       i < 4096      (the inverse NTT twiddle tables)
+    const Fp *xinv_hi;   // w_N^-(4096 i)
+};
+
+template <int LOG_F>
+__global__ void __launch_bounds__(256) fri_fold_kernel(const Fp *__restrict__ evals, Fp *__restrict__ out, int log_n, FoldParams P) {
+    constexpr int F = 1 << LOG_F;
+    const unsigned long long m = 1ull << (log_n - LOG_F);
+    const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    Fp v[F];
+#pragma unroll
+    for (int k = 0; k < F; ++k) v[k] = ld_fp(evals + i + (unsigned long long)k * m);
+    // inverse DFT of size F, decimation in frequency: natural in -> bit-reversed out
+#pragma unroll
+    for (int s = LOG_F - 1; s >= 0; --s) {
+        const int span = 1 << s;
+#pragma unroll
+        for (int k = 0; k < F; ++k) {
+            if (k & span) continue;
+            const int j = k & (span - 1);                 // twiddle exponent j * F / (2 span)
+            const Fp d = fp::sub4p(v[k], v[k + span]);
+            v[k] = fp::add(v[k], v[k + span]);
+            if (j == 0) { v[k + span] = d; fp::cond_sub_4p(v[k + span]); fp::cond_sub_2p(v[k + span]); }
+            else v[k + span] = fp::mul(d, P.winv[j << (LOG_F - 1 - s)]);
+        }
+    }
+    // t = alpha / x_i = (alpha / h) * w_N^-i ; Horner over c_j = IDFT_j / x^j (v holds IDFT in bit-reversed order)
+    Fp xinv = ld_fp(P.xinv_lo + (i & 4095ull));
+    if (i >> 12) xinv = fp::mul(xinv, ld_fp(P.xinv_hi + (i >> 12)));
+    const Fp t = fp::mul(xinv, P.alpha_hinv);
+    auto brev = [](int x) { int r = 0; for (int b = 0; b < LOG_F; ++b) r |= ((x >> b) & 1) << (LOG_F - 1 - b); return r; };
+    Fp acc = v[brev(F - 1)];
+#pragma unroll
+    for (int j = F - 2; j >= 0; --j) acc = fp::add(fp::mul(acc, t), v[brev(j)]);
+    acc = fp::mul(acc, P.scale);
+    st_fp(out + i, fp::canon(acc));
+}
+
+// ---- polynomial evaluation by pairwise folding --------------------------------------------------
+// One block folds 2048 contiguous values of one (column, point) job down to 1.  mult[l] is the
+// multiplier of fold level l of this launch (level 0 folds adjacent pairs).  Jobs along blockIdx.y.
+struct EvalJob {
+    const Fp *src;            // values of this job at this stage
+    Fp *dst;                  // one value per block
+    const Fp *mult;           // 11 multipliers for this stage (device memory)
+};
+
+__global__ void __launch_bounds__(256) poly_fold_kernel(const EvalJob *jobs, unsigned long long n_in, int levels) {
+    __shared__ Fp sm[256];
+    const EvalJob job = jobs[blockIdx.y];
+    const unsigned long long base = (unsigned long long)blockIdx.x * 2048ull + threadIdx.x * 8ull;
+    // levels: how many of the 11 levels are real (n_in may be < 2048 at the last stage)
+    Fp v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = (base + k < n_in) ? ld_fp(job.src + base + k) : fp::zero();
+    int lvl = 0;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+        if (lvl < levels) {
+            const Fp w = ld_fp(job.mult + lvl);
+#pragma unroll
+            for (int k = 0; k < (8 >> (s + 1)); ++k) v[k] = fp::add(v[2 * k], fp::mul(v[2 * k + 1], w));
+            ++lvl;
+        }
+    }
+    sm[threadIdx.x] = v[0];
+    __syncthreads();
+    for (int active = 128; active >= 1; active >>= 1) {
+        if (lvl < levels) {
+            Fp r;
+            if ((int)threadIdx.x < active) r = fp::add(sm[2 * threadIdx.x], fp::mul(sm[2 * threadIdx.x + 1], ld_fp(job.mult + lvl)));
+            __syncthreads();
+            if ((int)threadIdx.x < active) sm[threadIdx.x] = r;
+            __syncthreads();
+            ++lvl;
+        }
+    }
+    if (threadIdx.x == 0) st_fp(job.dst + blockIdx.x, fp::canon(sm[0]));
+}
+
+Fp host_root_of_unity(int log_n, bool inverse) {
+    uint32_t e[8] = {0, 0, 0, 0, 0, 0, 0x00000011u, 0x08000000u};
+    for (int s = 0; s < log_n; ++s)
+        for (int i = 0; i < 8; ++i) { e[i] >>= 1; if (i < 7) e[i] |= e[i + 1] << 31; }
+    Fp w = fp::pow_limbs(fp::from_u32(3), e, 8);
+    if (inverse) w = fp::inv(w);
+    return fp::canon(w);
+}
+void fill_inv_lo(Fp *dst, size_t n, int log_n, int) {
+    const Fp w = host_root_of_unity(log_n, true);
+    Fp c = fp::one();
+    for (size_t i = 0; i < n; ++i) { dst[i] = fp::canon(c); c = fp::mul(c, w); }
+}
+void fill_inv_hi(Fp *dst, size_t n, int log_n, int) {
+    const Fp w = fp::pow_u64(host_root_of_unity(log_n, true), 4096);
+    Fp c = fp::one();
+    for (size_t i = 0; i < n; ++i) { dst[i] = fp::canon(c); c = fp::mul(c, w); }
+}
+
+Fp load_host(const void *p) { Fp v; memcpy(v.l, p, 32); return v; }
+
+}  // namespace
+
+extern "C" {
+
+ss_status ss_fri_fold(ss_ctx *ctx, ss_field field, const void *d_evals, int log_n, int log_fold, const void *h_alpha,
+                      const void *h_domain_offset, int flags, void *d_out, void *stream) {
+    if (!ctx) return SS_ERR_INVALID;
+    if (field != SS_FIELD_FP252) return fail(ctx, SS_ERR_UNSUPPORTED, "ss_fri_fold: field %d not built", (int)field);
+    if (!d_evals || !d_out || !h_alpha || !h_domain_offset || log_fold < 1 || log_fold > 4 || log_n < log_fold || log_n > 40)
+        return fail(ctx, SS_ERR_INVALID, "ss_fri_fold: bad arguments (log_n=%d log_fold=%d)", log_n, log_fold);
+    SS_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+    const int F = 1 << log_fold;
+    FoldParams P;
+    const Fp wf_inv = host_root_of_unity(log_fold, true);
+    Fp c = fp::one();
+    for (int j = 0; j < 8; ++j) { P.winv[j] = fp::canon(c); if (j < F / 2) c = fp::mul(c, wf_inv); }
+    P.alpha_hinv = fp::canon(fp::mul(load_host(h_alpha), fp::inv(load_host(h_domain_offset))));
+    P.scale = (flags & 1) ? fp::one() : fp::canon(fp::inv(fp::from_u32((uint32_t)F)));
+    const size_t n = (size_t)1 << log_n;
+    Fp *lo, *hi;
+    ss_status rc;
+    // tables of w_N^-i : same contents as the inverse-NTT twiddle tables (keys shared with ntt_host.cu)
+    if ((rc = cached_table(ctx, {2 /*T_LO*/, log_n, 1}, n < 4096 ? n : 4096, fill_inv_lo, &lo))) return rc;
+    if ((rc = cached_table(ctx, {3 /*T_HI*/, log_n, 1}, n <= 4096 ? 1 : n / 4096, fill_inv_hi, &hi))) return rc;
+    P.xinv_lo = lo; P.xinv_hi = hi;
+    const unsigned long long m = 1ull << (log_n - log_fold);
+    const unsigned grid = (unsigned)((m + 255) / 256);
+    cudaStream_t st = pick_stream(ctx, stream);
+    const Fp *in = static_cast<const Fp *>(d_evals);
+    Fp *out = static_cast<Fp *>(d_out);
+    switch (log_fold) {
+    case 1: fri_fold_kernel<1><<<grid, 256, 0, st>>>(in, out, log_n, P); break;
+    case 2: fri_fold_kernel<2><<<grid, 256, 0, st>>>(in, out, log_n, P); break;
+    case 3: fri_fold_kernel<3><<<grid, 256, 0, st>>>(in, out, log_n, P); break;
+    default: fri_fold_kernel<4><<<grid, 256, 0, st>>>(in, out, log_n, P); break;
+    }
+    ctx->launches++;
+    SS_CUDA_CHECK(ctx, cudaGetLastError());
+    return SS_OK;
+}
+
+ss_status ss_poly_eval(ss_ctx *ctx, ss_field field, const void *d_coeffs, uint64_t coeff_stride, int log_n,
+                       const int32_t *h_cols, const void *h_points, size_t n_evals, void *h_out) {
+    if (!ctx) return SS_ERR_INVALID;
+    if (field != SS_FIELD_FP252) return fail(ctx, SS_ERR_UNSUPPORTED, "ss_poly_eval: field %d not built", (int)field);
+    if (!d_coeffs || log_n < 0 || log_n > 40 || (n_evals && (!h_cols || !h_points || !h_out)) || coeff_stride < (1ull << log_n))
+        return fail(ctx, SS_ERR_INVALID, "ss_poly_eval: bad arguments");
+    if (n_evals == 0) return SS_OK;
+    SS_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+    const unsigned long long n = 1ull << log_n;
+    const Fp *coeffs = static_cast<const Fp *>(d_coeffs);
+    const Fp ginv = fp::inv(fp::from_u32(3));
+    // multipliers per job: level l (0 = adjacent pairs) uses w^(n / 2^(l+1)), w = z / 3
+    std::vector<Fp> mults(n_evals * (size_t)(log_n ? log_n : 1));
+    for (size_t e = 0; e < n_evals; ++e) {
+        const Fp w = fp::mul(load_host(static_cast<const uint8_t *>(h_points) + 32 * e), ginv);
+        Fp pw = fp::canon(w);                                  // w^(2^0)
+        for (int l = log_n - 1; l >= 0; --l) {                // level l needs w^(2^(log_n-1-l))
+            mults[e * log_n + l] = pw;
+            pw = fp::canon(fp::sqr(pw));
+        }
+    }
+    // stage buffers: ping-pong of ceil(n/2048) partials per job
+    const unsigned long long part0 = (n + 2047) / 2048;
+    Fp *d_mult = nullptr, *d_a = nullptr, *d_b = nullptr;
+    EvalJob *d_jobs = nullptr;
+    cudaError_t ce = cudaMalloc(&d_mult, mults.size() * sizeof(Fp));
+    if (ce == cudaSuccess) ce = cudaMalloc(&d_a, n_evals * part0 * sizeof(Fp));
+    if (ce == cudaSuccess) ce = cudaMalloc(&d_b, n_evals * ((part0 + 2047) / 2048) * sizeof(Fp));
+    if (ce == cudaSuccess) ce = cudaMalloc(&d_jobs, n_evals * sizeof(EvalJob));
+    if (ce != cudaSuccess) {
+        cudaFree(d_mult); cudaFree(d_a); cudaFree(d_b); cudaFree(d_jobs);
+        return fail(ctx, SS_ERR_OOM, "ss_poly_eval: %s", cudaGetErrorString(ce));
+    }
+    cudaMemcpy(d_mult, mults.data(), mults.size() * sizeof(Fp), cudaMemcpyHostToDevice);
+    std::vector<EvalJob> jobs(n_evals);
+    unsigned long long n_in = n;
+    int level = 0;
+    Fp *cur_out = d_a, *other = d_b;
+    const Fp *final_src = nullptr;
+    bool first = true;
+    while (true) {
+        const unsigned long long blocks = (n_in + 2047) / 2048;
+        const int levels = (log_n - level) < 11 ? (log_n - level) : 11;
+        for (size_t e = 0; e < n_evals; ++e) {
+            jobs[e].src = first ? coeffs + (unsigned long long)h_cols[e] * coeff_stride : (cur_out == d_a ? d_b : d_a) + e * n_in;
+            jobs[e].dst = cur_out + e * blocks;
+            jobs[e].mult = d_mult + e * (size_t)(log_n ? log_n : 1) + level;
+        }
+        cudaMemcpy(d_jobs, jobs.data(), n_evals * sizeof(EvalJob), cudaMemcpyHostToDevice);
+        dim3 grid((unsigned)blocks, (unsigned)n_evals, 1);
+        poly_fold_kernel<<<grid, 256>>>(d_jobs, n_in, levels);
+        ctx->launches++;
+        level += levels;
+        final_src = cur_out;
+        n_in = blocks;
+        first = false;
+        if (level >= log_n) break;
+        Fp *t = cur_out; cur_out = other; other = t;
+    }
+    // n_in == 1 per job now (blocks of the last stage == 1)
+    std::vector<Fp> res(n_evals);
+    ce = cudaMemcpy(res.data(), final_src, n_evals * sizeof(Fp), cudaMemcpyDeviceToHost);
+    cudaFree(d_mult); cudaFree(d_a); cudaFree(d_b); cudaFree(d_jobs);
+    if (ce != cudaSuccess) return fail(ctx, SS_ERR_CUDA, "ss_poly_eval: %s", cudaGetErrorString(ce));
+    memcpy(h_out, res.data(), n_evals * sizeof(Fp));
+    return SS_OK;
+}
+
+}  // extern "C"

@@ -84,3 +84,34 @@ class Matrix:
                              ctypes.c_void_p(coeffs.data_ptr()) if keep_coeffs else None, n, out_order, _stream_ptr()))
         lde = Matrix(out, c)
         return (lde, Matrix(coeffs, c)) if keep_coeffs else lde
+
+
+# ---- FRI / OOD helpers (ministark FriProver::build_layers, DeepPolyComposer inputs) --------------
+def _felt_bytes(value_mont_limbs) -> bytes:
+    return np.ascontiguousarray(value_mont_limbs, dtype=np.uint64).tobytes()
+
+
+def fri_fold(evals: torch.Tensor, log_fold: int, alpha_mont: np.ndarray, offset_mont: np.ndarray, starkware_scale: bool = False,
+             ctx: Context | None = None) -> torch.Tensor:
+    """evals: int64[N, 4] on the coset offset*<w_N> (natural order) -> int64[N >> log_fold, 4]."""
+    ctx = ctx or default_context(evals.device.index)
+    n = evals.shape[0]
+    out = torch.empty((n >> log_fold, 4), dtype=torch.int64, device=evals.device)
+    a, h = _felt_bytes(alpha_mont), _felt_bytes(offset_mont)
+    ctx.check(ctx.lib.ss_fri_fold(ctx.handle, _lib.FIELD_FP252, ctypes.c_void_p(evals.data_ptr()), n.bit_length() - 1, log_fold,
+                                  a, h, int(starkware_scale), ctypes.c_void_p(out.data_ptr()), _stream_ptr()))
+    return out
+
+
+def poly_eval(coeffs: "Matrix", cols, points_mont: np.ndarray) -> np.ndarray:
+    """coeffs: the coefficient matrix returned by Matrix.lde(keep_coeffs=True); evaluates column cols[e]
+    at points_mont[e] (Montgomery limbs).  Returns uint64[len, 4]."""
+    ctx = coeffs.ctx
+    cols = np.ascontiguousarray(cols, dtype=np.int32)
+    pts = np.ascontiguousarray(points_mont, dtype=np.uint64).reshape(-1, 4)
+    out = np.zeros_like(pts)
+    torch.cuda.current_stream().synchronize()
+    ctx.check(ctx.lib.ss_poly_eval(ctx.handle, _lib.FIELD_FP252, ctypes.c_void_p(coeffs.data.data_ptr()), coeffs.num_rows, coeffs.log_rows,
+                                   cols.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), pts.ctypes.data_as(ctypes.c_void_p), len(cols),
+                                   out.ctypes.data_as(ctypes.c_void_p)))
+    return out
