@@ -190,21 +190,23 @@ class HotPath:
                                ctypes.c_void_p(dst[j].data_ptr()), self.N, None, 0, ss.ORDER_NATURAL, None))
 
     def _owned(self, n_cols):
-        return [j for j in range(n_cols) if j % self.world == self.rank]
+        from sandstorm_b200.parallel import owned_columns
+
+        return owned_columns(n_cols, self.rank, self.world)
 
     def _share(self, buf, n_cols):
-        if self.world == 1:
-            return
-        import torch.distributed as dist
+        from sandstorm_b200.parallel import share_columns
 
-        for j in range(n_cols):                      # NCCL broadcast of each LDE column from its owner
-            dist.broadcast(buf[j], src=j % self.world)
+        share_columns(buf, self.world)               # NCCL broadcast of each LDE column from its owner
 
     def _commit(self, lde, kind):
         """Merkle over this rank's row range (whole matrix at world == 1)."""
         ss = self.ss
-        rows = self.N // self.world
-        sub = lde[:, self.rank * rows:(self.rank + 1) * rows]
+        from sandstorm_b200.parallel import row_range
+
+        lo, hi = row_range(self.N, self.rank, self.world)
+        rows = hi - lo
+        sub = lde[:, lo:hi]
         c = self.ctx
         handle = ctypes.c_void_p()
         c.check(c.lib.ss_merkle_build(c.handle, kind, 0, ctypes.c_void_p(sub.data_ptr()), self.N, lde.shape[0],
@@ -280,12 +282,10 @@ class ShardTree:
         c.check(c.lib.ss_merkle_root(c.handle, self.handle, out))
         if hp.world == 1:
             return bytes(out)
-        import torch.distributed as dist
+        from sandstorm_b200.parallel import gather_subroots
 
-        mine = torch.tensor(list(out), dtype=torch.uint8, device="cuda")
-        allr = torch.empty((hp.world, 32), dtype=torch.uint8, device="cuda")
-        dist.all_gather_into_tensor(allr, mine)
-        sub = (ctypes.c_uint8 * (32 * hp.world)).from_buffer_copy(allr.cpu().numpy().tobytes())
+        roots = gather_subroots(bytes(out), hp.world, "cuda")
+        sub = (ctypes.c_uint8 * (32 * hp.world)).from_buffer_copy(b"".join(roots))
         c.check(c.lib.ss_merkle_combine(c.handle, self.kind, sub, hp.world.bit_length() - 1, out))
         return bytes(out)
 
