@@ -112,6 +112,7 @@ def cpu_oracle_run(steps: int, warmup: int, log_n: int = 18, n_cols: int = 2):
     import oracle
 
     oracle.build()
+    oracle.set_threads(os.cpu_count() or 1)       # torchrun pins OMP_NUM_THREADS=1
     rng = np.random.default_rng(0xB200)
     cols = oracle.random_felts(rng, n_cols, 1 << log_n)
     ops = lde_ops(n_cols, log_n)

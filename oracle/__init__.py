@@ -121,6 +121,11 @@ def num_threads() -> int:
     return int(lib().oracle_num_threads())
 
 
+def set_threads(n: int) -> None:
+    """torchrun exports OMP_NUM_THREADS=1; the CPU baseline wants every host core."""
+    lib().oracle_set_threads(ctypes.c_int(int(n)))
+
+
 # ----------------------------------------------------------------------- hashes
 def hash_bytes(kind: int, data: bytes) -> bytes:
     out = ctypes.create_string_buffer(32)

@@ -10,7 +10,7 @@ import os
 from ctypes import POINTER, c_char_p, c_int, c_size_t, c_uint8, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsandstorm_b200.so")
+LIB_PATH = os.environ.get("SS_LIB_PATH") or os.path.join(_HERE, "libsandstorm_b200.so")   # SS_LIB_PATH: A/B kernel variants
 
 SS_OK, SS_ERR_INVALID, SS_ERR_CUDA, SS_ERR_OOM, SS_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 FIELD_FP252, FIELD_GOLDILOCKS = 0, 1

@@ -1,0 +1,21 @@
+"""Runs a compiled composition-constraint program on a device-resident LDE matrix
+(the GPU replacement of ministark's `AirConfig::eval_constraint`)."""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from .. import _lib
+from ..matrix import Matrix, _stream_ptr
+from .program import CompiledProgram
+
+
+def evaluate(program: CompiledProgram, lde: Matrix, log_blowup: int) -> torch.Tensor:
+    """lde: all trace columns (base then extension) on the LDE coset, natural order.
+    Returns int64[N, 4]: the composition evaluations on the same coset."""
+    c = lde.ctx
+    out = torch.empty((lde.num_rows, 4), dtype=torch.int64, device=lde.data.device)
+    c.check(c.lib.ss_constraint_eval(c.handle, program.blob, len(program.blob), ctypes.c_void_p(lde.data.data_ptr()), lde.num_rows,
+                                     lde.num_cols, lde.log_rows - log_blowup, log_blowup, ctypes.c_void_p(out.data_ptr()), _stream_ptr()))
+    return out

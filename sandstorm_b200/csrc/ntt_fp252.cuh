@@ -14,7 +14,13 @@
 
 namespace ss {
 
-constexpr int NTT_LOG_TILE = 12;
+#ifndef SS_NTT_LOG_TILE
+#define SS_NTT_LOG_TILE 12
+#endif
+#ifndef SS_NTT_MIN_CTAS
+#define SS_NTT_MIN_CTAS 1
+#endif
+constexpr int NTT_LOG_TILE = SS_NTT_LOG_TILE;
 constexpr int NTT_TILE = 1 << NTT_LOG_TILE;
 constexpr int NTT_THREADS = NTT_TILE / 8;
 constexpr int NTT_SMEM_BYTES = NTT_TILE * 32;
@@ -137,7 +143,7 @@ __device__ __forceinline__ void stage(Fp (&x)[8], int base, int q, int q0, int L
 
 // One pass.  grid = (tiles per column [or tiles over all columns when n < 4096], n_cols or 1).
 template <bool DIT>
-__global__ void __launch_bounds__(NTT_THREADS, 1) ntt_pass_kernel(const NttPass P) {
+__global__ void __launch_bounds__(NTT_THREADS, SS_NTT_MIN_CTAS) ntt_pass_kernel(const NttPass P) {
     extern __shared__ uint4 smem_raw[];
     nttk::Smem sm{smem_raw, smem_raw + NTT_TILE};
     const int t = threadIdx.x;

@@ -32,7 +32,8 @@ void geometric(Fp *dst, size_t n, Fp c, const Fp &h) {
     }
 }
 
-void fill_local(Fp *dst, size_t n, int, int inverse) { geometric(dst, n, fp::one(), root_of_unity(NTT_LOG_TILE, inverse != 0)); }
+// local twiddles are always powers of w_4096 (2048 entries), whatever the tile size
+void fill_local(Fp *dst, size_t n, int, int inverse) { geometric(dst, n, fp::one(), root_of_unity(12, inverse != 0)); }
 void fill_lo(Fp *dst, size_t n, int log_n, int inverse) { geometric(dst, n, fp::one(), root_of_unity(log_n, inverse != 0)); }
 void fill_hi(Fp *dst, size_t n, int log_n, int inverse) {
     const Fp w = root_of_unity(log_n, inverse != 0);
@@ -111,7 +112,7 @@ ss_status run_ntt(ss_ctx *ctx, const NttJob &job, cudaStream_t st) {
     Fp *tw_local, *tw_lo, *tw_hi, *sc_lo = nullptr, *sc_hi = nullptr;
     ss_status rc;
     const size_t n = (size_t)1 << job.log_n;
-    if ((rc = cached_table(ctx, {T_LOCAL, NTT_LOG_TILE, inv}, 2048, fill_local, &tw_local))) return rc;
+    if ((rc = cached_table(ctx, {T_LOCAL, 12, inv}, 2048, fill_local, &tw_local))) return rc;
     if ((rc = cached_table(ctx, {T_LO, job.log_n, inv}, n < 4096 ? n : 4096, fill_lo, &tw_lo))) return rc;
     if ((rc = cached_table(ctx, {T_HI, job.log_n, inv}, n <= 4096 ? 1 : n / 4096, fill_hi, &tw_hi))) return rc;
     if (job.pre_scale != SCALE_NONE || job.post_scale != SCALE_NONE) {

@@ -1,0 +1,119 @@
+"""GPU parity: ss_constraint_eval vs the independent big-int tree evaluator on the LDE of a random trace."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ss():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import sandstorm_b200
+
+    return sandstorm_b200
+
+
+@pytest.mark.parametrize("log_n,log_blowup", [(3, 1), (5, 2), (10, 1), (13, 1)])
+def test_toy_air_composition_matches_tree_evaluator(ss, oracle, log_n, log_blowup):
+    import torch
+
+    from air_ref import eval_expr
+    from sandstorm_b200.air import compile_program, composition_constraint
+    from sandstorm_b200.air.evaluate import evaluate
+    from test_air_compile import toy_air
+
+    rng = np.random.default_rng(900 + log_n)
+    n, N = 1 << log_n, 1 << (log_n + log_blowup)
+    trace = oracle.random_felts(rng, 3, n)
+    lde = ss.Matrix.from_numpy(trace).lde(log_blowup)
+    lde_np = lde.numpy()
+    assert np.array_equal(lde_np, oracle.lde(trace, log_blowup))
+    challenges = [int.from_bytes(rng.bytes(31), "big") for _ in range(2)]
+    hints = [int.from_bytes(rng.bytes(31), "big") for _ in range(2)]
+    alpha = [int.from_bytes(rng.bytes(31), "big")]
+    expr = composition_constraint(toy_air(n))
+    prog = compile_program(expr, log_n, log_blowup, challenges, hints, alpha)
+    got = evaluate(prog, lde, log_blowup)
+    torch.cuda.synchronize()
+    got_int = oracle.from_mont(got.cpu().numpy().view(np.uint64))
+    rows = list(range(N)) if N <= 128 else [0, 1, 2, 3, 5, 8, N // 2, N // 2 + 1, N - 9, N - 2, N - 1] + [int(x) for x in rng.integers(0, N, 12)]
+    cols_int = None
+    if N <= 128:
+        cols_int = [oracle.from_mont(lde_np[c]) for c in range(3)]
+    for i in rows:
+        if cols_int is None:
+            # only the tapped rows are needed: offsets 0..5 (x blowup)
+            need = sorted({(i + k * (1 << log_blowup)) % N for k in range(6)})
+            sparse = [dict(zip(need, oracle.from_mont(lde_np[c][need]))) for c in range(3)]
+
+            class Col(dict):
+                def __getitem__(self, k):
+                    return dict.__getitem__(self, k % N)
+
+            view = [Col(s) for s in sparse]
+        else:
+            view = cols_int
+        assert got_int[i] == eval_expr(expr, i, view, log_n, log_blowup, challenges, hints, alpha), i
+
+
+def test_rejects_malformed_programs(ss, oracle):
+    import ctypes
+
+    import torch
+
+    from sandstorm_b200.air import Trace, compile_program
+
+    prog = compile_program(Trace(0, 0) * Trace(0, 1), 3, 1)
+    d = torch.zeros((1, 16, 4), dtype=torch.int64, device="cuda")
+    out = torch.zeros((16, 4), dtype=torch.int64, device="cuda")
+    c = ss.default_context()
+    bad = bytearray(prog.blob)
+    bad[0] ^= 0xFF
+    assert c.lib.ss_constraint_eval(c.handle, bytes(bad), len(bad), ctypes.c_void_p(d.data_ptr()), 16, 1, 3, 1, ctypes.c_void_p(out.data_ptr()), None) == -1
+    # wrong size / wrong log_n
+    assert c.lib.ss_constraint_eval(c.handle, prog.blob, len(prog.blob) - 32, ctypes.c_void_p(d.data_ptr()), 16, 1, 3, 1, ctypes.c_void_p(out.data_ptr()), None) == -1
+    assert c.lib.ss_constraint_eval(c.handle, prog.blob, len(prog.blob), ctypes.c_void_p(d.data_ptr()), 32, 1, 4, 1, ctypes.c_void_p(out.data_ptr()), None) == -1
+
+
+def test_deep_composition_matches_definition(ss, oracle):
+    """DEEP quotient over the LDE domain: with y_t the true evaluations the result is a polynomial of
+    degree < n - 1 (checked through the inverse NTT), and every sampled row matches the big-int formula."""
+    import torch
+
+    from sandstorm_b200.air import compile_program
+    from sandstorm_b200.air.deep import deep_expr
+    from sandstorm_b200.air.evaluate import evaluate
+    from sandstorm_b200.matrix import poly_eval
+
+    P = oracle.P
+    rng = np.random.default_rng(77)
+    log_n, log_b, n_cols = 8, 1, 4
+    n, N = 1 << log_n, 1 << (log_n + log_b)
+    trace = oracle.random_felts(rng, n_cols, n)
+    lde, coeffs = ss.Matrix.from_numpy(trace).lde(log_b, keep_coeffs=True)
+    g = pow(3, (P - 1) // n, P)
+    z = int.from_bytes(rng.bytes(31), "big")
+    alpha = int.from_bytes(rng.bytes(31), "big")
+    offsets = [0, 1, 2, 5, 16, 17, 33, 100, 255] + list(range(40, 90))          # > 32 distinct points: exercises the batch limit
+    taps = [(c, off) for c in range(n_cols) for off in offsets[: 20 + 10 * c]]
+    pts = [z * pow(g, off, P) % P for _, off in taps]
+    ys = oracle.from_mont(poly_eval(coeffs, [c for c, _ in taps], oracle.to_mont(pts)))
+    terms = [(c, pt, y, pow(alpha, k, P)) for k, ((c, _), pt, y) in enumerate(zip(taps, pts, ys))]
+    prog = compile_program(deep_expr(terms), log_n, log_b)
+    assert prog.n_batch_inv == len(set(pts))
+    got = evaluate(prog, lde, log_b)
+    torch.cuda.synchronize()
+    got_np = got.cpu().numpy().view(np.uint64)
+    lde_int = [oracle.from_mont(col) for col in lde.numpy()]
+    w = pow(3, (P - 1) // N, P)
+    for i in [0, 1, 7, N // 2, N - 1, 123]:
+        x = 3 * pow(w, i, P) % P
+        want = sum(a * (lde_int[c][i] - y) * pow(x - pt, -1, P) for c, pt, y, a in terms) % P
+        assert oracle.from_mont(got_np[i:i + 1])[0] == want
+    # low-degree check: interpolate the N evaluations on the coset; coefficients >= n - 1 must vanish
+    m = ss.Matrix(got.reshape(1, N, 4).contiguous())
+    c = oracle.from_mont(m.ntt_(inverse=True, coset=True).numpy()[0])
+    assert all(v == 0 for v in c[n - 1:]) and any(v != 0 for v in c[: n - 1])
