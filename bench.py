@@ -51,8 +51,11 @@ def lde_ops(n_cols: int, log_n: int) -> float:
     return n_cols * (ntt_ops(log_n) + ntt_ops(log_n + LOG_BLOWUP))
 
 
+NTT_LOG_TILE = 11                           # csrc/ntt_fp252.cuh SS_NTT_LOG_TILE
+
+
 def plan_passes(log_n: int) -> int:
-    return 1 if log_n <= 12 else -(-log_n // 12)
+    return 1 if log_n <= NTT_LOG_TILE else -(-log_n // NTT_LOG_TILE)
 
 
 def lde_algo_bytes(n_cols: int, log_n: int) -> float:

@@ -1,6 +1,7 @@
 // Batched Fp252 NTT for sm_100a: multi-pass "four-step" decomposition, each pass = one kernel that
-// stages a 4096-element tile (128 KB) in shared memory and runs up to 12 radix-2 stages on it with
-// register radix-8 rounds (8 elements per thread, 512 threads, conflict-free swizzled smem).
+// stages a 2^NTT_LOG_TILE-element tile (2048 elements = 64 KB, two CTAs per SM) in shared memory and
+// runs up to NTT_LOG_TILE radix-2 stages on it with register radix-8 rounds (8 elements per thread,
+// conflict-free swizzled smem).
 //
 //   DIF (natural -> bit-reversed):  top bits first; strided tiles; post-multiply by the inter-pass
 //        twiddle w_B^(lo * brev_L(m)); last pass contiguous tiles.
@@ -14,11 +15,13 @@
 
 namespace ss {
 
+// Tile geometry (A/B measured on B200, profiles/r01_ntt_tile_ab.md): 2048-element tiles with two
+// resident CTAs per SM beat 4096 x 1, 1024 x 4 and 512 x 8.
 #ifndef SS_NTT_LOG_TILE
-#define SS_NTT_LOG_TILE 12
+#define SS_NTT_LOG_TILE 11
 #endif
 #ifndef SS_NTT_MIN_CTAS
-#define SS_NTT_MIN_CTAS 1
+#define SS_NTT_MIN_CTAS 2
 #endif
 constexpr int NTT_LOG_TILE = SS_NTT_LOG_TILE;
 constexpr int NTT_TILE = 1 << NTT_LOG_TILE;
