@@ -117,3 +117,41 @@ def test_deep_composition_matches_definition(ss, oracle):
     m = ss.Matrix(got.reshape(1, N, 4).contiguous())
     c = oracle.from_mont(m.ntt_(inverse=True, coset=True).numpy()[0])
     assert all(v == 0 for v in c[n - 1:]) and any(v != 0 for v in c[: n - 1])
+
+
+@pytest.mark.parametrize("name,log_n", [("recursive", 12), ("starknet", 15)])
+def test_layout_composition_on_gpu(ss, oracle, name, log_n):
+    """The real Cairo AIRs (transpiled from layouts/src/*/air.rs): GPU evaluation of the composition
+    constraint on the LDE of a random trace vs the independent tree evaluator at sampled rows."""
+    import random
+
+    import torch
+
+    from air_ref import eval_expr
+    from sandstorm_b200.air import compile_program
+    from sandstorm_b200.air.evaluate import evaluate
+    from sandstorm_b200.air.layouts import load_layout
+
+    L = load_layout(name)
+    rnd = random.Random(log_n)
+    P = oracle.P
+    n, N = 1 << log_n, 2 << log_n
+    rng = np.random.default_rng(log_n)
+    lde_np = oracle.random_felts(rng, L.num_columns, N)           # any matrix: the evaluator does not need a valid trace
+    lde = ss.Matrix.from_numpy(lde_np)
+    ch = [rnd.randrange(P) for _ in range(L.n_challenges())]
+    hints = [rnd.randrange(P) for _ in range(L.n_hints())]
+    alpha = [rnd.randrange(P)]
+    expr = L.composition(n)
+    prog = compile_program(expr, log_n, 1, ch, hints, alpha)
+    got = evaluate(prog, lde, 1)
+    torch.cuda.synchronize()
+    got_np = got.cpu().numpy().view(np.uint64)
+    taps = L.taps()
+    for i in [0, 1, 2, 15, 16, 31, N // 2, N - 1, N - 2 * L.max_offset - 1] + [rnd.randrange(N) for _ in range(6)]:
+        i %= N
+        cols = [dict() for _ in range(L.num_columns)]
+        for c, off in taps:
+            r = (i + 2 * off) % N
+            cols[c][r] = oracle.from_mont(lde_np[c][r:r + 1])[0]
+        assert oracle.from_mont(got_np[i:i + 1])[0] == eval_expr(expr, i, cols, log_n, 1, ch, hints, alpha), (name, i)
