@@ -134,9 +134,9 @@ ss_status ss_rows_gather(ss_ctx *ctx, const void *d_cols, uint64_t col_stride, i
 ss_status ss_fri_fold(ss_ctx *ctx, ss_field field, const void *d_evals, int log_n, int log_fold,
                       const void *h_alpha, const void *h_domain_offset, int flags, void *d_out, void *stream);
 /* Out-of-domain evaluations (trace / composition polynomials at z * g^k): for e < n_evals,
- * h_out[e] = poly_{h_cols[e]}(h_points[e]), polynomials given by the coefficient matrix ss_lde writes
- * (coset-scaled, bit-reversed).  Synchronises. */
-ss_status ss_poly_eval(ss_ctx *ctx, ss_field field, const void *d_coeffs, uint64_t coeff_stride, int log_n,
+ * h_out[e] = poly_{h_cols[e]}(h_points[e]).  natural_order = 0: the coefficient matrix ss_lde writes
+ * (coset-scaled, bit-reversed); 1: plain coefficients in natural order (composition columns).  Synchronises. */
+ss_status ss_poly_eval(ss_ctx *ctx, ss_field field, const void *d_coeffs, uint64_t coeff_stride, int log_n, int natural_order,
                        const int32_t *h_cols, const void *h_points, size_t n_evals, void *h_out);
 
 /* ------------------------------------------------------------------ constraint evaluation (§8 a4-a7)

@@ -365,10 +365,18 @@ def compile_program(expr: Expr, log_n: int, log_blowup: int, challenges=(), hint
             n_slots += 1
             pinned.add(base + k)
         for k, iv in enumerate(batch):
-            s = emit(iv[1])
-            # move into the pinned slot with an ADDC 0 (rare: a handful of boundary denominators)
+            den = iv[1]
+            s = emit(den)
+            # move into the pinned slot (ADDC 0); the denominator's own slot is recycled at once — if it
+            # is also used as a plain factor later it is recomputed (one subtraction)
             code.append((OP_ADDC, base + k, s, const_id(0), 0))
-            release(iv[1])
+            if den[0] in LEAVES:
+                release(den)
+            else:
+                uses[den] -= 1
+                if s not in pinned:
+                    free.append(s)
+                slot_of.pop(den, None)
             slot_of[iv] = base + k
         code.append((OP_BATCHINV, 0, base, len(batch), 0))
         stats["mul"] += 262 + 3 * (len(batch) - 1)

@@ -19,8 +19,12 @@ using namespace ss;
 namespace {
 
 enum Op : uint32_t { OP_NOP, OP_CONST, OP_TRACE, OP_TABLE, OP_X, OP_ADD, OP_SUB, OP_MUL, OP_NEG, OP_INV, OP_BATCHINV, OP_OUT, OP_MULC, OP_ADDC };
-constexpr int MAX_SLOTS = 256;     // per-thread slot file (local memory, L1-resident for typical programs)
-constexpr int MAX_BATCH = 192;     // denominators inverted together (boundary terms; DEEP has one per OOD point)
+// two instantiations: constraint compositions need ~32 slots and a handful of boundary denominators;
+// DEEP compositions pin one denominator per out-of-domain point (191 + 1 for the starknet layout)
+constexpr int MAX_SLOTS = 256;
+constexpr int MAX_BATCH = 192;
+constexpr int SMALL_SLOTS = 64;
+constexpr int SMALL_BATCH = 32;
 constexpr uint32_t MAGIC = 0x50435353u;
 constexpr int T_XLO = 20, T_XHI = 21;
 
@@ -45,11 +49,12 @@ __device__ __forceinline__ Fp ldg_fp(const Fp *p) {
     return v;
 }
 
+template <int SLOTS, int BATCH>
 __global__ void __launch_bounds__(128) constraint_eval_kernel(const EvalArgs A) {
     const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     const unsigned long long N = 1ull << A.log_N;
     if (i >= N) return;
-    Fp s[MAX_SLOTS];
+    Fp s[SLOTS];
 #pragma unroll 1
     for (int pc = 0; pc < A.n_instr; ++pc) {
         const uint4 ins = __ldg(A.code + pc);
@@ -82,7 +87,7 @@ __global__ void __launch_bounds__(128) constraint_eval_kernel(const EvalArgs A) 
         case OP_INV: s[d] = ec::inv_chain(s[a]); break;
         case OP_BATCHINV: {
             // Montgomery's trick over slots [a, a + b)
-            Fp pre[MAX_BATCH];
+            Fp pre[BATCH];
             Fp acc = fp::one();
             for (uint32_t k = 0; k < b; ++k) { pre[k] = acc; acc = fp::mul(acc, s[a + k]); }
             Fp inv = ec::inv_chain(acc);
@@ -190,7 +195,13 @@ ss_status ss_constraint_eval(ss_ctx *ctx, const void *h_program, size_t program_
     A.log_N = log_N;
     A.xlo = xlo; A.xhi = xhi;
     A.out = static_cast<Fp *>(d_out);
-    constraint_eval_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(A);
+    uint32_t max_batch = 0;
+    for (uint32_t pc = 0; pc < n_instr; ++pc)
+        if ((code[4 * pc] & 0xff) == OP_BATCHINV && code[4 * pc + 2] > max_batch) max_batch = code[4 * pc + 2];
+    if (n_slots <= (uint32_t)SMALL_SLOTS && max_batch <= (uint32_t)SMALL_BATCH)
+        constraint_eval_kernel<SMALL_SLOTS, SMALL_BATCH><<<(unsigned)((N + 127) / 128), 128, 0, st>>>(A);
+    else
+        constraint_eval_kernel<MAX_SLOTS, MAX_BATCH><<<(unsigned)((N + 127) / 128), 128, 0, st>>>(A);
     ctx->launches++;
     SS_CUDA_CHECK(ctx, cudaGetLastError());
     SS_CUDA_CHECK(ctx, cudaFreeAsync(d_prog, st));

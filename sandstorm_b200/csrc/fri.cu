@@ -179,7 +179,7 @@ ss_status ss_fri_fold(ss_ctx *ctx, ss_field field, const void *d_evals, int log_
     return SS_OK;
 }
 
-ss_status ss_poly_eval(ss_ctx *ctx, ss_field field, const void *d_coeffs, uint64_t coeff_stride, int log_n,
+ss_status ss_poly_eval(ss_ctx *ctx, ss_field field, const void *d_coeffs, uint64_t coeff_stride, int log_n, int natural_order,
                        const int32_t *h_cols, const void *h_points, size_t n_evals, void *h_out) {
     if (!ctx) return SS_ERR_INVALID;
     if (field != SS_FIELD_FP252) return fail(ctx, SS_ERR_UNSUPPORTED, "ss_poly_eval: field %d not built", (int)field);
@@ -190,13 +190,15 @@ ss_status ss_poly_eval(ss_ctx *ctx, ss_field field, const void *d_coeffs, uint64
     const unsigned long long n = 1ull << log_n;
     const Fp *coeffs = static_cast<const Fp *>(d_coeffs);
     const Fp ginv = fp::inv(fp::from_u32(3));
-    // multipliers per job: level l (0 = adjacent pairs) uses w^(n / 2^(l+1)), w = z / 3
+    // multipliers per job.  ss_lde format (coefficient k scaled by 3^k at position brev(k)): level l
+    // (0 = adjacent pairs) uses w^(n / 2^(l+1)) with w = z / 3.  Natural order, plain coefficients:
+    // adjacent pairs are (a[2m], a[2m+1]) -> a[2m] + z a[2m+1], so level l uses z^(2^l).
     std::vector<Fp> mults(n_evals * (size_t)(log_n ? log_n : 1));
     for (size_t e = 0; e < n_evals; ++e) {
-        const Fp w = fp::mul(load_host(static_cast<const uint8_t *>(h_points) + 32 * e), ginv);
-        Fp pw = fp::canon(w);                                  // w^(2^0)
-        for (int l = log_n - 1; l >= 0; --l) {                // level l needs w^(2^(log_n-1-l))
-            mults[e * log_n + l] = pw;
+        const Fp z = load_host(static_cast<const uint8_t *>(h_points) + 32 * e);
+        Fp pw = fp::canon(natural_order ? z : fp::mul(z, ginv));
+        for (int s2 = 0; s2 < log_n; ++s2) {                  // pw = w^(2^s2)
+            mults[e * log_n + (natural_order ? s2 : log_n - 1 - s2)] = pw;
             pw = fp::canon(fp::sqr(pw));
         }
     }

@@ -103,15 +103,16 @@ def fri_fold(evals: torch.Tensor, log_fold: int, alpha_mont: np.ndarray, offset_
     return out
 
 
-def poly_eval(coeffs: "Matrix", cols, points_mont: np.ndarray) -> np.ndarray:
-    """coeffs: the coefficient matrix returned by Matrix.lde(keep_coeffs=True); evaluates column cols[e]
-    at points_mont[e] (Montgomery limbs).  Returns uint64[len, 4]."""
+def poly_eval(coeffs: "Matrix", cols, points_mont: np.ndarray, natural_order: bool = False) -> np.ndarray:
+    """coeffs: the coefficient matrix returned by Matrix.lde(keep_coeffs=True) (or, with natural_order, plain
+    natural-order coefficients); evaluates column cols[e] at points_mont[e] (Montgomery limbs).
+    Returns uint64[len, 4]."""
     ctx = coeffs.ctx
     cols = np.ascontiguousarray(cols, dtype=np.int32)
     pts = np.ascontiguousarray(points_mont, dtype=np.uint64).reshape(-1, 4)
     out = np.zeros_like(pts)
     torch.cuda.current_stream().synchronize()
     ctx.check(ctx.lib.ss_poly_eval(ctx.handle, _lib.FIELD_FP252, ctypes.c_void_p(coeffs.data.data_ptr()), coeffs.num_rows, coeffs.log_rows,
-                                   cols.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), pts.ctypes.data_as(ctypes.c_void_p), len(cols),
+                                   int(natural_order), cols.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), pts.ctypes.data_as(ctypes.c_void_p), len(cols),
                                    out.ctypes.data_as(ctypes.c_void_p)))
     return out
