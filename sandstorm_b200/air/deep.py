@@ -25,3 +25,29 @@ def deep_expr(terms) -> Expr:
         q = num / (X - Constant(z))
         total = q if total is None else total + q
     return total
+
+
+def deep_expr_shifted(trace_terms, comp_terms, u_col: int, v_col: int, g: int, p: int) -> Expr:
+    """Same polynomial, with every denominator read from two precomputed columns instead of inverted per row:
+
+        u[i] = 1 / (x_i - z)      (column u_col)        v[i] = 1 / (x_i - z^ce)     (column v_col)
+        1 / (x_i - z g^off) = g^-off * u[i - blowup * off]            (x_i - z g^off = g^off (x_{i - b off} - z))
+
+    trace_terms: (column, offset, claimed value y, coefficient);  comp_terms: (column, y, coefficient).
+    `Trace(u_col, -off)` is a row offset in TRACE units, i.e. -off * blowup LDE rows, exactly the shift above."""
+    by_off: dict[int, Expr] = {}
+    for col, off, y, coeff in trace_terms:
+        term = Constant(coeff) * (Trace(col, 0) - Constant(y))
+        by_off[off] = term if off not in by_off else by_off[off] + term
+    total = None
+    for off, num in by_off.items():
+        q = num * Constant(pow(g, -off, p)) * Trace(u_col, -off)
+        total = q if total is None else total + q
+    comp = None
+    for col, y, coeff in comp_terms:
+        term = Constant(coeff) * (Trace(col, 0) - Constant(y))
+        comp = term if comp is None else comp + term
+    if comp is not None:
+        q = comp * Trace(v_col, 0)
+        total = q if total is None else total + q
+    return total

@@ -48,14 +48,37 @@ class Layout:
             m = max(m, spec["interval"])
         return m
 
-    def constraints(self, n: int) -> list[Expr]:
+    def constraints(self, n: int, inv_x_minus_one_col: int | None = None) -> list[Expr]:
+        """inv_x_minus_one_col: index of an auxiliary matrix column holding w[i] = 1 / (x_i - 1)
+        (ss_inv_x_minus_c with c = 1).  Divisions by the boundary terms X - g^e are then rewritten as
+        g^-e * w[i - blowup * e] — a shifted read instead of a per-row inversion
+        (x_i - g^e = g^e (x_{i - b e} - 1))."""
         if n & (n - 1) or n < self.min_trace_len():
             raise ValueError(f"trace length {n} is not a power of two >= {self.min_trace_len()}")
         g = pow(3, (P - 1) // n, P)
         coeffs = _periodic_coeffs()
         built: list[Expr] = []
-        for k in self._nodes:
+        nodes = self._nodes
+
+        def boundary_exponent(idx):
+            """e if node idx is X - g^e, else None."""
+            k = nodes[idx]
+            if k[0] != "sub" or nodes[k[1]][0] != "x":
+                return None
+            c = nodes[k[2]]
+            if c[0] == "gpow":
+                return (c[1] * n // c[2] + c[3]) % n
+            if c[0] == "const" and int(c[1], 16) == 1:
+                return 0
+            return None
+
+        for k in nodes:
             op = k[0]
+            if op == "div" and inv_x_minus_one_col is not None:
+                e_b = boundary_exponent(k[2])
+                if e_b is not None:
+                    built.append(built[k[1]] * Constant(pow(g, -e_b, P)) * Trace(inv_x_minus_one_col, -e_b))
+                    continue
             if op == "x": e = X
             elif op == "const": e = Constant(int(k[1], 16))
             elif op == "gpow": e = Constant(pow(g, (k[1] * n // k[2] + k[3]) % n, P))
@@ -74,8 +97,8 @@ class Layout:
             built.append(e)
         return [built[i] for i in self._constraints]
 
-    def composition(self, n: int) -> Expr:
-        return composition_constraint(self.constraints(n))
+    def composition(self, n: int, inv_x_minus_one_col: int | None = None) -> Expr:
+        return composition_constraint(self.constraints(n, inv_x_minus_one_col))
 
     def n_challenges(self) -> int:
         return 1 + max((k[1] for k in self._nodes if k[0] == "challenge"), default=-1)

@@ -117,6 +117,65 @@ __global__ void __launch_bounds__(256) poly_fold_kernel(const EvalJob *jobs, uns
     if (threadIdx.x == 0) st_fp(job.dst + blockIdx.x, fp::canon(sm[0]));
 }
 
+// ---- out[i] = 1 / (h * w_N^i - c) for every i: Montgomery batch inversion, R rows per thread ----------
+// Every denominator X - c * g^e of the AIR boundary terms and of the DEEP quotients is a shifted read of
+// this one vector:  x_i - c g^e = g^e (x_{i - b e} - c)  (g = w_N^b generates the trace domain).
+constexpr int INV_ROWS = 16;
+__global__ void __launch_bounds__(128) inv_x_minus_c_kernel(Fp *out, int log_n, Fp c, const Fp *xlo, const Fp *xhi) {
+    const unsigned long long n = 1ull << log_n;
+    const unsigned long long chunk = (unsigned long long)blockDim.x * INV_ROWS;
+    const unsigned long long base = blockIdx.x * chunk + threadIdx.x;     // rows base + k * blockDim.x: coalesced stores
+    Fp d[INV_ROWS], pre[INV_ROWS];
+    Fp acc = fp::one();
+#pragma unroll
+    for (int k = 0; k < INV_ROWS; ++k) {
+        const unsigned long long i = base + (unsigned long long)k * blockDim.x;
+        Fp x = fp::one();
+        if (i < n) {
+            x = ld_fp(xlo + (i & 4095ull));
+            if (i >> 12) x = fp::mul(x, ld_fp(xhi + (i >> 12)));
+            x = fp::sub(x, c);
+        }
+        d[k] = x;
+        pre[k] = acc;
+        acc = fp::mul(acc, x);
+    }
+    // inverse of the running product: a^(p-2), p - 2 = (2^59 + 2^4) * 2^192 + (2^192 - 1)
+    auto sqn = [](Fp v, int m) { for (int t = 0; t < m; ++t) v = fp::sqr(v); return v; };
+    const Fp e2 = fp::mul(sqn(acc, 1), acc), e4 = fp::mul(sqn(e2, 2), e2), e8 = fp::mul(sqn(e4, 4), e4);
+    const Fp e16 = fp::mul(sqn(e8, 8), e8), e32 = fp::mul(sqn(e16, 16), e16), e64 = fp::mul(sqn(e32, 32), e32);
+    const Fp e128 = fp::mul(sqn(e64, 64), e64), e192 = fp::mul(sqn(e128, 64), e64);
+    const Fp gq = fp::mul(e192, acc);
+    Fp inv = fp::mul(sqn(fp::mul(sqn(gq, 55), gq), 4), e192);
+#pragma unroll
+    for (int k = INV_ROWS - 1; k >= 0; --k) {
+        const unsigned long long i = base + (unsigned long long)k * blockDim.x;
+        const Fp t = fp::mul(inv, pre[k]);
+        inv = fp::mul(inv, d[k]);
+        if (i < n) st_fp(out + i, fp::canon(t));
+    }
+}
+
+void fill_x_lo(Fp *dst, size_t n, int log_n, int h) {
+    Fp w = fp::one();
+    {   // w_N
+        uint32_t e[8] = {0, 0, 0, 0, 0, 0, 0x00000011u, 0x08000000u};
+        for (int s = 0; s < log_n; ++s)
+            for (int i = 0; i < 8; ++i) { e[i] >>= 1; if (i < 7) e[i] |= e[i + 1] << 31; }
+        w = fp::canon(fp::pow_limbs(fp::from_u32(3), e, 8));
+    }
+    Fp c = fp::from_u32((uint32_t)h);
+    for (size_t i = 0; i < n; ++i) { dst[i] = fp::canon(c); c = fp::mul(c, w); }
+}
+void fill_x_hi(Fp *dst, size_t n, int log_n, int) {
+    uint32_t e[8] = {0, 0, 0, 0, 0, 0, 0x00000011u, 0x08000000u};
+    for (int s = 0; s < log_n; ++s)
+        for (int i = 0; i < 8; ++i) { e[i] >>= 1; if (i < 7) e[i] |= e[i + 1] << 31; }
+    const Fp w = fp::pow_u64(fp::canon(fp::pow_limbs(fp::from_u32(3), e, 8)), 4096);
+    Fp c = fp::one();
+    for (size_t i = 0; i < n; ++i) { dst[i] = fp::canon(c); c = fp::mul(c, w); }
+}
+
 Fp host_root_of_unity(int log_n, bool inverse) {
     uint32_t e[8] = {0, 0, 0, 0, 0, 0, 0x00000011u, 0x08000000u};
     for (int s = 0; s < log_n; ++s)
@@ -174,6 +233,24 @@ ss_status ss_fri_fold(ss_ctx *ctx, ss_field field, const void *d_evals, int log_
     case 3: fri_fold_kernel<3><<<grid, 256, 0, st>>>(in, out, log_n, P); break;
     default: fri_fold_kernel<4><<<grid, 256, 0, st>>>(in, out, log_n, P); break;
     }
+    ctx->launches++;
+    SS_CUDA_CHECK(ctx, cudaGetLastError());
+    return SS_OK;
+}
+
+ss_status ss_inv_x_minus_c(ss_ctx *ctx, ss_field field, int log_n, const void *h_c, void *d_out, void *stream) {
+    if (!ctx) return SS_ERR_INVALID;
+    if (field != SS_FIELD_FP252) return fail(ctx, SS_ERR_UNSUPPORTED, "ss_inv_x_minus_c: field %d not built", (int)field);
+    if (!h_c || !d_out || log_n < 0 || log_n > 40) return fail(ctx, SS_ERR_INVALID, "ss_inv_x_minus_c: bad arguments");
+    SS_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)1 << log_n;
+    Fp *lo, *hi;
+    ss_status rc;
+    // x_i = 3 * w_N^i: same tables (and cache keys) as the constraint evaluator's OP_X
+    if ((rc = cached_table(ctx, {20, log_n, 0}, n < 4096 ? n : 4096, [](Fp *d, size_t m, int ln, int) { fill_x_lo(d, m, ln, 3); }, &lo))) return rc;
+    if ((rc = cached_table(ctx, {21, log_n, 0}, n <= 4096 ? 1 : n / 4096, fill_x_hi, &hi))) return rc;
+    const unsigned long long chunk = 128ull * INV_ROWS;
+    inv_x_minus_c_kernel<<<(unsigned)((n + chunk - 1) / chunk), 128, 0, pick_stream(ctx, stream)>>>(static_cast<Fp *>(d_out), log_n, fp::canon(load_host(h_c)), lo, hi);
     ctx->launches++;
     SS_CUDA_CHECK(ctx, cudaGetLastError());
     return SS_OK;

@@ -116,3 +116,12 @@ def poly_eval(coeffs: "Matrix", cols, points_mont: np.ndarray, natural_order: bo
                                    int(natural_order), cols.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), pts.ctypes.data_as(ctypes.c_void_p), len(cols),
                                    out.ctypes.data_as(ctypes.c_void_p)))
     return out
+
+
+def inv_x_minus_c(out: torch.Tensor, c_mont: np.ndarray, ctx: Context | None = None) -> torch.Tensor:
+    """out[i] = 1 / (3 * w_N^i - c) for the N = out.shape[0] points of the LDE coset (ss_inv_x_minus_c)."""
+    ctx = ctx or default_context(out.device.index)
+    n = out.shape[0]
+    ctx.check(ctx.lib.ss_inv_x_minus_c(ctx.handle, _lib.FIELD_FP252, n.bit_length() - 1, _felt_bytes(c_mont),
+                                       ctypes.c_void_p(out.data_ptr()), _stream_ptr()))
+    return out

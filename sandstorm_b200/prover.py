@@ -26,11 +26,11 @@ import torch
 
 from . import _lib
 from .air import compile_program
-from .air.deep import deep_expr
+from .air.deep import deep_expr_shifted
 from .air.evaluate import evaluate
 from .air.expr import P
 from .air.layouts import load_layout
-from .matrix import Matrix, fri_fold, poly_eval
+from .matrix import Matrix, fri_fold, inv_x_minus_c, poly_eval
 from .merkle import MatrixMerkleTree
 
 R = 2**256
@@ -71,6 +71,9 @@ class HotPathProver:
         self.rnd = random.Random(seed)
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.g = pow(3, (P - 1) // self.n, P)
+        # columns of the working matrix: trace | composition (ce) | w = 1/(x-1) | u = 1/(x-z) | v = 1/(x-z^ce)
+        C = self.layout.num_columns
+        self.comp_col, self.w_col, self.u_col, self.v_col = C, C + self.ce, C + self.ce + 1, C + self.ce + 2
         self._composition_program = None
         self._challenges = self._hints = self._alpha = None
         self.timeline: list = []
@@ -91,8 +94,9 @@ class HotPathProver:
             self._challenges = [self._draw() for _ in range(L.n_challenges())]
             self._hints = [self._draw() for _ in range(L.n_hints())]
             self._alpha = [self._draw()]
-            self._composition_program = compile_program(L.composition(self.n), self.log_n, self.opt.log_blowup,
-                                                        self._challenges, self._hints, self._alpha)
+            # boundary denominators X - g^e read the auxiliary column w = 1/(x - 1) (see Layout.constraints)
+            self._composition_program = compile_program(L.composition(self.n, inv_x_minus_one_col=self.w_col), self.log_n,
+                                                        self.opt.log_blowup, self._challenges, self._hints, self._alpha)
         return self._composition_program
 
     # ---- the device stages ---------------------------------------------------------------------------------
@@ -106,7 +110,7 @@ class HotPathProver:
         # 3-5: base trace
         # one matrix for every committed column: trace columns first, the ce composition columns last
         # (the DEEP stage reads all of them; a single allocation avoids a 50 GB concatenation at 2^22 steps)
-        all_lde = torch.empty((L.num_columns + self.ce, N, 4), dtype=torch.int64, device=dev)
+        all_lde = torch.empty((L.num_columns + self.ce + 3, N, 4), dtype=torch.int64, device=dev)
         lde = all_lde[: L.num_columns]
         coeffs = torch.empty((L.num_columns, n, 4), dtype=torch.int64, device=dev)
         c = base.ctx
@@ -128,15 +132,15 @@ class HotPathProver:
         self.mark("merkle_ext")
         # 9: constraint evaluation
         prog = self.composition_program()
-        lde_m = Matrix(lde, c)
-        comp_evals = evaluate(prog, lde_m, b)
+        inv_x_minus_c(all_lde[self.w_col], _mont(1), c)
+        comp_evals = evaluate(prog, Matrix(all_lde, c), b)
         self.mark("constraint_eval")
         # 10: composition polynomial -> ce columns (coefficients j, j+ce, ...) -> LDE -> commit
         work = Matrix(comp_evals.view(1, N, 4), c)
         work.ntt_(inverse=True, coset=True)
         self.mark("ntt_comp_inv")
         comp_coeffs = comp_evals.view(n, self.ce, 4).permute(1, 0, 2).contiguous()        # [ce, n, 4] natural order
-        comp_lde = all_lde[L.num_columns:]
+        comp_lde = all_lde[self.comp_col:self.comp_col + self.ce]
         comp_lde.zero_()
         comp_lde[:, :n] = comp_coeffs
         self.mark("comp_split")
@@ -157,12 +161,14 @@ class HotPathProver:
         res.ood_trace, res.ood_composition = from_m(ood), from_m(ood_c)
         # 12: DEEP composition over the LDE coset (coefficients = powers of one alpha, src/lib.rs:102-116)
         alpha = self._draw()
-        terms, k = [], 0
-        for (col, _), pt, y in zip(taps, pts, res.ood_trace):
-            terms.append((col, pt, y, pow(alpha, k, P))); k += 1
+        t_terms, c_terms, k = [], [], 0
+        for (col, off), y in zip(taps, res.ood_trace):
+            t_terms.append((col, off, y, pow(alpha, k, P))); k += 1
         for j, y in enumerate(res.ood_composition):
-            terms.append((L.num_columns + j, zc, y, pow(alpha, k, P))); k += 1
-        deep_prog = compile_program(deep_expr(terms), self.log_n, b)
+            c_terms.append((self.comp_col + j, y, pow(alpha, k, P))); k += 1
+        inv_x_minus_c(all_lde[self.u_col], _mont(z), c)
+        inv_x_minus_c(all_lde[self.v_col], _mont(zc), c)
+        deep_prog = compile_program(deep_expr_shifted(t_terms, c_terms, self.u_col, self.v_col, self.g, P), self.log_n, b)
         del coeffs, comp_coeffs, comp_evals, work
         deep = evaluate(deep_prog, Matrix(all_lde, c), b)
         self.mark("deep")

@@ -155,3 +155,38 @@ def test_layout_composition_on_gpu(ss, oracle, name, log_n):
             r = (i + 2 * off) % N
             cols[c][r] = oracle.from_mont(lde_np[c][r:r + 1])[0]
         assert oracle.from_mont(got_np[i:i + 1])[0] == eval_expr(expr, i, cols, log_n, 1, ch, hints, alpha), (name, i)
+
+
+def test_shifted_inverse_rewrite_is_equivalent(ss, oracle):
+    """1/(x_i - g^e) = g^-e * w[i - 2e] with w = 1/(x - 1): the rewritten recursive-layout program (no per-row
+    inversion) gives the same composition evaluations as the direct one; and ss_inv_x_minus_c matches big ints."""
+    import random
+
+    import torch
+
+    from sandstorm_b200.air import compile_program
+    from sandstorm_b200.air.evaluate import evaluate
+    from sandstorm_b200.air.layouts import load_layout
+    from sandstorm_b200.matrix import inv_x_minus_c
+
+    P = oracle.P
+    L = load_layout("recursive")
+    log_n = 12
+    n, N = 1 << log_n, 2 << log_n
+    rnd = random.Random(4)
+    rng = np.random.default_rng(4)
+    cols = torch.zeros((L.num_columns + 1, N, 4), dtype=torch.int64, device="cuda")
+    cols[: L.num_columns] = torch.from_numpy(oracle.random_felts(rng, L.num_columns, N).view(np.int64)).cuda()
+    inv_x_minus_c(cols[L.num_columns], oracle.to_mont([1])[0])
+    w = pow(3, (P - 1) // N, P)
+    got_w = oracle.from_mont(cols[L.num_columns].cpu().numpy().view(np.uint64))
+    for i in (0, 1, 5, N // 2, N - 1):
+        assert got_w[i] == pow(3 * pow(w, i, P) - 1, -1, P)
+    ch, hints, alpha = [rnd.randrange(P) for _ in range(6)], [rnd.randrange(P) for _ in range(L.n_hints())], [rnd.randrange(P)]
+    m = ss.Matrix(cols)
+    direct = evaluate(compile_program(L.composition(n), log_n, 1, ch, hints, alpha), m, 1)
+    prog = compile_program(L.composition(n, inv_x_minus_one_col=L.num_columns), log_n, 1, ch, hints, alpha)
+    assert prog.n_batch_inv == 0
+    shifted = evaluate(prog, m, 1)
+    torch.cuda.synchronize()
+    assert torch.equal(direct, shifted)
