@@ -281,11 +281,11 @@ class HotPath:
 
 
 class FullHotPath(HotPath):
-    """world == 1: every device stage of the prove loop (sandstorm_b200/prover.py) with the real starknet AIR."""
+    """Every device stage of the prove loop (sandstorm_b200/prover.py) with the real starknet AIR, on 1..8 ranks."""
 
     NTT_STAGES = ("lde_base", "lde_ext", "ntt_comp_inv", "ntt_comp_fwd")
 
-    def __init__(self, log_n: int, seed: int = 0xB200):
+    def __init__(self, log_n: int, rank: int = 0, world: int = 1, seed: int = 0xB200):
         import torch
 
         import sandstorm_b200 as ss
@@ -294,7 +294,7 @@ class FullHotPath(HotPath):
         self.torch, self.ss = torch, ss
         self.log_n, self.log_N = log_n, log_n + LOG_BLOWUP
         self.n, self.N = 1 << log_n, 1 << (log_n + LOG_BLOWUP)
-        self.rank, self.world = 0, 1
+        self.rank, self.world = rank, world
         dev = torch.device("cuda", torch.cuda.current_device())
         g = torch.Generator(device=dev).manual_seed(seed)
 
@@ -305,7 +305,7 @@ class FullHotPath(HotPath):
 
         self.base, self.ext = rand_cols(N_BASE, self.n), rand_cols(N_EXT, self.n)
         self.ctx = ss.default_context()
-        self.prover = HotPathProver("starknet", log_n)
+        self.prover = HotPathProver("starknet", log_n, rank=rank, world=world)
         t0 = time.perf_counter()
         self.program = self.prover.composition_program()        # host-side compile, outside every timed region
         self.compile_s = time.perf_counter() - t0
@@ -380,10 +380,10 @@ def gpu_arm(args):
     while need(log_n) > 0.85 * free_b and log_n > 12:
         log_n -= 1
     need_full = lambda ln: 32.0 * ((N_BASE + N_EXT) * (1 << ln) * 2 + (N_BASE + N_EXT + N_COMP + 3) * (2 << ln) + 4 * (2 << ln) + 3 * 2 * (2 << ln)) + 6e9
-    if world == 1 and not args.partial:
+    if not args.partial:
         while need_full(log_n) > 0.9 * free_b and log_n > 15:
             log_n -= 1
-        hp = FullHotPath(log_n)
+        hp = FullHotPath(log_n, rank, world)
     else:
         hp = HotPath(log_n, rank, world)
     ctx = hp.ctx
@@ -482,7 +482,7 @@ def gpu_arm(args):
         "ms_per_step": ms_per_step, "prove_seconds": ms_per_step / 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u256 (Fp252 Montgomery, 8 x u32 limbs)", "data": "synthetic",
         "config": {"workload": f"starknet layout, 2^{log_n - CYCLE_HEIGHT_LOG} Cairo steps (n=2^{log_n} rows, LDE 2^{log_n + LOG_BLOWUP}), Fp252, {N_BASE}+{N_EXT} trace + {N_COMP} composition columns, masked-Keccak Merkle",
-                   "requested_log_steps": args.log_steps, "parallelism": f"columns sharded over {world} rank(s), row-range Merkle", "l2": "inputs_larger_than_L2",
+                   "requested_log_steps": args.log_steps, "parallelism": f"{world} rank(s): LDE + OOD sharded by column (NCCL broadcast / all-reduce), Merkle + constraint eval + DEEP + FRI folds by LDE row range (all-gather, combined sub-roots); composition-column NTTs replicated", "l2": "inputs_larger_than_L2",
                    "stages_in_step": list(stages.keys()),
                    "not_in_step": [] if isinstance(hp, FullHotPath) else ["constraint_eval (stand-in column)", "ood", "deep_composition", "fri_layers", "queries"],
                    "air": "starknet layout, 195 constraints (sandstorm_b200/air/layouts/starknet.json)" if isinstance(hp, FullHotPath) else None,
@@ -508,7 +508,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log-steps", type=int, default=22, help="log2 of Cairo steps (22 = BASELINE metric config; n = 16 * steps)")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--partial", action="store_true", help="N=1 only: LDE + commits with a stand-in composition column (the N>1 step)")
+    ap.add_argument("--partial", action="store_true", help="LDE + commits only, with a stand-in composition column")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -130,9 +130,12 @@ ss_status ss_rows_gather(ss_ctx *ctx, const void *d_cols, uint64_t col_stride, i
  *   f(x) = sum_{j<F} x^j F_j(x^F)   ->   out[i] = sum_j alpha^j F_j(x_i^F),   i < N/F.
  * flags bit 0: multiply by F (StarkWare's binary folds with alpha, alpha^2, alpha^4 and no 1/2).
  * The layer's commitment is ss_merkle_build(d_evals, col_stride = N/F, n_cols = F, log_rows = log_n - log_fold):
- * row i of the reference's FRI layer matrix is (e[i], e[i + N/F], ...), i.e. the buffer itself. */
+ * row i of the reference's FRI layer matrix is (e[i], e[i + N/F], ...), i.e. the buffer itself.
+ * out_begin / out_count select the outputs [out_begin, out_begin + out_count) (count 0 = all): the
+ * row range one GPU folds when a layer is sharded by rows; d_out is indexed by the absolute output row. */
 ss_status ss_fri_fold(ss_ctx *ctx, ss_field field, const void *d_evals, int log_n, int log_fold,
-                      const void *h_alpha, const void *h_domain_offset, int flags, void *d_out, void *stream);
+                      const void *h_alpha, const void *h_domain_offset, int flags, uint64_t out_begin,
+                      uint64_t out_count, void *d_out, void *stream);
 /* d_out[i] = 1 / (x_i - c) for every point x_i = 3 * w_N^i of the LDE coset (N = 2^log_n), one batched
  * inversion per 16 rows.  Because x_i - c g^e = g^e (x_{i - b e} - c) for the trace-domain generator
  * g = w_N^b, every boundary denominator X - g^e of the AIR (c = 1) and every DEEP denominator
@@ -150,7 +153,8 @@ ss_status ss_poly_eval(ss_ctx *ctx, ss_field field, const void *d_coeffs, uint64
  * into straight-line code; format in sandstorm_b200/air/program.py) on every LDE row.          */
 ss_status ss_constraint_eval(ss_ctx *ctx, const void *h_program, size_t program_bytes,
                              const void *d_lde_cols, uint64_t col_stride, int n_cols, int log_n,
-                             int log_blowup, void *d_out, void *stream);
+                             int log_blowup, uint64_t row_begin, uint64_t row_count /* 0 = all rows */,
+                             void *d_out /* indexed by absolute row */, void *stream);
 
 #ifdef __cplusplus
 }

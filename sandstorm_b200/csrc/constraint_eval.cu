@@ -39,6 +39,7 @@ struct EvalArgs {
     int log_N;
     const Fp *xlo, *xhi;       // 3 * w_N^i (i < 4096), w_N^(4096 i)
     Fp *out;
+    unsigned long long row_begin, row_count;   // rows [row_begin, row_begin + row_count) of the LDE domain
 };
 
 __device__ __forceinline__ Fp ldg_fp(const Fp *p) {
@@ -51,9 +52,10 @@ __device__ __forceinline__ Fp ldg_fp(const Fp *p) {
 
 template <int SLOTS, int BATCH>
 __global__ void __launch_bounds__(128) constraint_eval_kernel(const EvalArgs A) {
-    const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    const unsigned long long t = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     const unsigned long long N = 1ull << A.log_N;
-    if (i >= N) return;
+    if (t >= A.row_count) return;
+    const unsigned long long i = A.row_begin + t;
     Fp s[SLOTS];
 #pragma unroll 1
     for (int pc = 0; pc < A.n_instr; ++pc) {
@@ -132,7 +134,8 @@ void fill_xhi(Fp *dst, size_t n, int log_n, int) {
 extern "C" {
 
 ss_status ss_constraint_eval(ss_ctx *ctx, const void *h_program, size_t program_bytes, const void *d_lde_cols,
-                             uint64_t col_stride, int n_cols, int log_n, int log_blowup, void *d_out, void *stream) {
+                             uint64_t col_stride, int n_cols, int log_n, int log_blowup, uint64_t row_begin, uint64_t row_count,
+                             void *d_out, void *stream) {
     if (!ctx) return SS_ERR_INVALID;
     if (!h_program || program_bytes < 32 || !d_lde_cols || !d_out || n_cols < 1)
         return fail(ctx, SS_ERR_INVALID, "ss_constraint_eval: bad arguments");
@@ -195,13 +198,16 @@ ss_status ss_constraint_eval(ss_ctx *ctx, const void *h_program, size_t program_
     A.log_N = log_N;
     A.xlo = xlo; A.xhi = xhi;
     A.out = static_cast<Fp *>(d_out);
+    if (row_count == 0) { row_begin = 0; row_count = N; }                 // 0 = the whole domain
+    if (row_begin + row_count > N) return fail(ctx, SS_ERR_INVALID, "ss_constraint_eval: row range outside the domain");
+    A.row_begin = row_begin; A.row_count = row_count;
     uint32_t max_batch = 0;
     for (uint32_t pc = 0; pc < n_instr; ++pc)
         if ((code[4 * pc] & 0xff) == OP_BATCHINV && code[4 * pc + 2] > max_batch) max_batch = code[4 * pc + 2];
     if (n_slots <= (uint32_t)SMALL_SLOTS && max_batch <= (uint32_t)SMALL_BATCH)
-        constraint_eval_kernel<SMALL_SLOTS, SMALL_BATCH><<<(unsigned)((N + 127) / 128), 128, 0, st>>>(A);
+        constraint_eval_kernel<SMALL_SLOTS, SMALL_BATCH><<<(unsigned)((row_count + 127) / 128), 128, 0, st>>>(A);
     else
-        constraint_eval_kernel<MAX_SLOTS, MAX_BATCH><<<(unsigned)((N + 127) / 128), 128, 0, st>>>(A);
+        constraint_eval_kernel<MAX_SLOTS, MAX_BATCH><<<(unsigned)((row_count + 127) / 128), 128, 0, st>>>(A);
     ctx->launches++;
     SS_CUDA_CHECK(ctx, cudaGetLastError());
     SS_CUDA_CHECK(ctx, cudaFreeAsync(d_prog, st));

@@ -41,11 +41,13 @@ struct FoldParams {
 };
 
 template <int LOG_F>
-__global__ void __launch_bounds__(256) fri_fold_kernel(const Fp *__restrict__ evals, Fp *__restrict__ out, int log_n, FoldParams P) {
+__global__ void __launch_bounds__(256) fri_fold_kernel(const Fp *__restrict__ evals, Fp *__restrict__ out, int log_n, FoldParams P,
+                                                         unsigned long long out_begin, unsigned long long out_count) {
     constexpr int F = 1 << LOG_F;
     const unsigned long long m = 1ull << (log_n - LOG_F);
-    const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-    if (i >= m) return;
+    const unsigned long long tid = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (tid >= out_count) return;
+    const unsigned long long i = out_begin + tid;
     Fp v[F];
 #pragma unroll
     for (int k = 0; k < F; ++k) v[k] = ld_fp(evals + i + (unsigned long long)k * m);
@@ -202,7 +204,7 @@ Fp load_host(const void *p) { Fp v; memcpy(v.l, p, 32); return v; }
 extern "C" {
 
 ss_status ss_fri_fold(ss_ctx *ctx, ss_field field, const void *d_evals, int log_n, int log_fold, const void *h_alpha,
-                      const void *h_domain_offset, int flags, void *d_out, void *stream) {
+                      const void *h_domain_offset, int flags, uint64_t out_begin, uint64_t out_count, void *d_out, void *stream) {
     if (!ctx) return SS_ERR_INVALID;
     if (field != SS_FIELD_FP252) return fail(ctx, SS_ERR_UNSUPPORTED, "ss_fri_fold: field %d not built", (int)field);
     if (!d_evals || !d_out || !h_alpha || !h_domain_offset || log_fold < 1 || log_fold > 4 || log_n < log_fold || log_n > 40)
@@ -223,15 +225,17 @@ ss_status ss_fri_fold(ss_ctx *ctx, ss_field field, const void *d_evals, int log_
     if ((rc = cached_table(ctx, {3 /*T_HI*/, log_n, 1}, n <= 4096 ? 1 : n / 4096, fill_inv_hi, &hi))) return rc;
     P.xinv_lo = lo; P.xinv_hi = hi;
     const unsigned long long m = 1ull << (log_n - log_fold);
-    const unsigned grid = (unsigned)((m + 255) / 256);
+    if (out_count == 0) { out_begin = 0; out_count = m; }                 // 0 = every output
+    if (out_begin + out_count > m) return fail(ctx, SS_ERR_INVALID, "ss_fri_fold: output range outside the folded domain");
+    const unsigned grid = (unsigned)((out_count + 255) / 256);
     cudaStream_t st = pick_stream(ctx, stream);
     const Fp *in = static_cast<const Fp *>(d_evals);
     Fp *out = static_cast<Fp *>(d_out);
     switch (log_fold) {
-    case 1: fri_fold_kernel<1><<<grid, 256, 0, st>>>(in, out, log_n, P); break;
-    case 2: fri_fold_kernel<2><<<grid, 256, 0, st>>>(in, out, log_n, P); break;
-    case 3: fri_fold_kernel<3><<<grid, 256, 0, st>>>(in, out, log_n, P); break;
-    default: fri_fold_kernel<4><<<grid, 256, 0, st>>>(in, out, log_n, P); break;
+    case 1: fri_fold_kernel<1><<<grid, 256, 0, st>>>(in, out, log_n, P, out_begin, out_count); break;
+    case 2: fri_fold_kernel<2><<<grid, 256, 0, st>>>(in, out, log_n, P, out_begin, out_count); break;
+    case 3: fri_fold_kernel<3><<<grid, 256, 0, st>>>(in, out, log_n, P, out_begin, out_count); break;
+    default: fri_fold_kernel<4><<<grid, 256, 0, st>>>(in, out, log_n, P, out_begin, out_count); break;
     }
     ctx->launches++;
     SS_CUDA_CHECK(ctx, cudaGetLastError());

@@ -92,14 +92,17 @@ def _felt_bytes(value_mont_limbs) -> bytes:
 
 
 def fri_fold(evals: torch.Tensor, log_fold: int, alpha_mont: np.ndarray, offset_mont: np.ndarray, starkware_scale: bool = False,
-             ctx: Context | None = None) -> torch.Tensor:
-    """evals: int64[N, 4] on the coset offset*<w_N> (natural order) -> int64[N >> log_fold, 4]."""
+             ctx: Context | None = None, out: torch.Tensor | None = None, rows: tuple[int, int] | None = None) -> torch.Tensor:
+    """evals: int64[N, 4] on the coset offset*<w_N> (natural order) -> int64[N >> log_fold, 4].
+    rows = (begin, count): fold only those outputs (the row range of one rank), written at their absolute position."""
     ctx = ctx or default_context(evals.device.index)
     n = evals.shape[0]
-    out = torch.empty((n >> log_fold, 4), dtype=torch.int64, device=evals.device)
+    if out is None:
+        out = torch.empty((n >> log_fold, 4), dtype=torch.int64, device=evals.device)
     a, h = _felt_bytes(alpha_mont), _felt_bytes(offset_mont)
+    begin, count = rows if rows is not None else (0, 0)
     ctx.check(ctx.lib.ss_fri_fold(ctx.handle, _lib.FIELD_FP252, ctypes.c_void_p(evals.data_ptr()), n.bit_length() - 1, log_fold,
-                                  a, h, int(starkware_scale), ctypes.c_void_p(out.data_ptr()), _stream_ptr()))
+                                  a, h, int(starkware_scale), begin, count, ctypes.c_void_p(out.data_ptr()), _stream_ptr()))
     return out
 
 

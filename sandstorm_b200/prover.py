@@ -31,7 +31,6 @@ from .air.evaluate import evaluate
 from .air.expr import P
 from .air.layouts import load_layout
 from .matrix import Matrix, fri_fold, inv_x_minus_c, poly_eval
-from .merkle import MatrixMerkleTree
 
 R = 2**256
 
@@ -63,12 +62,16 @@ class HotPathResult:
 
 
 class HotPathProver:
-    def __init__(self, layout: str, log_n: int, options: ProofOptions | None = None, seed: int = 0xB200, device=None):
+    def __init__(self, layout: str, log_n: int, options: ProofOptions | None = None, seed: int = 0xB200, device=None,
+                 rank: int = 0, world: int = 1):
         self.layout = load_layout(layout)
         self.log_n, self.opt = log_n, options or ProofOptions()
         self.n, self.N = 1 << log_n, 1 << (log_n + self.opt.log_blowup)
         self.ce = 1 << self.opt.log_blowup                      # ce_blowup_factor == lde blowup for Cairo (degree-2 constraints)
-        self.rnd = random.Random(seed)
+        self.rnd = random.Random(seed)           # same seed on every rank: identical challenges everywhere
+        self.rank, self.world = rank, world
+        if world & (world - 1):
+            raise ValueError("world size must be a power of two")
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.g = pow(3, (P - 1) // self.n, P)
         # columns of the working matrix: trace | composition (ce) | w = 1/(x-1) | u = 1/(x-z) | v = 1/(x-z^ce)
@@ -99,41 +102,84 @@ class HotPathProver:
                                                         self.opt.log_blowup, self._challenges, self._hints, self._alpha)
         return self._composition_program
 
+    # ---- commitment helper: whole tree on one GPU, row-range sub-trees + combined root on several ---------
+    def _commit(self, ptr: int, col_stride: int, n_cols: int, log_rows: int):
+        """Returns (root bytes, handle or None).  ptr: device address of column 0, row 0 of the matrix."""
+        c, opt = self.ctx, self.opt
+        world, rank = self.world, self.rank
+        shard = world > 1 and log_rows - (world.bit_length() - 1) >= 10
+        rows = 1 << log_rows
+        lo, cnt = (rank * (rows // world), rows // world) if shard else (0, rows)
+        handle = ctypes.c_void_p()
+        c.check(c.lib.ss_merkle_build(c.handle, opt.tree_kind, 0, ctypes.c_void_p(ptr + 32 * lo), col_stride, n_cols,
+                                      cnt.bit_length() - 1, _lib.ORDER_NATURAL, ctypes.byref(handle), None))
+        root = (ctypes.c_uint8 * 32)()
+        c.check(c.lib.ss_merkle_root(c.handle, handle, root))
+        if shard:
+            from .parallel import gather_subroots
+
+            subs = gather_subroots(bytes(root), world, self.device)
+            buf = (ctypes.c_uint8 * (32 * world)).from_buffer_copy(b"".join(subs))
+            c.check(c.lib.ss_merkle_combine(c.handle, opt.tree_kind, buf, world.bit_length() - 1, root))
+        return bytes(root), handle
+
+    def _gather_rows(self, full: torch.Tensor, lo: int, cnt: int):
+        """all-gather of a row-sharded vector: every rank contributes full[lo:lo+cnt]."""
+        if self.world == 1:
+            return
+        import torch.distributed as dist
+
+        dist.all_gather_into_tensor(full, full[lo:lo + cnt].clone())
+
     # ---- the device stages ---------------------------------------------------------------------------------
     def prove(self, base: Matrix, ext: Matrix, queries: bool = True) -> HotPathResult:
+        """base / ext: the trace columns (every rank holds them: they come from the host-side trace builder).
+        With world > 1 (torch.distributed initialised, one process per GPU): LDE and OOD are sharded by column,
+        Merkle hashing / constraint evaluation / DEEP / FRI folds by LDE row range; LDE columns are broadcast
+        from their owners, row-sharded vectors all-gathered, sub-tree roots combined (SURVEY.md §8e plan A)."""
         opt, L = self.opt, self.layout
         assert base.num_cols == L.num_base_columns and ext.num_cols == L.num_extension_columns and base.num_rows == self.n
+        from .parallel import owned_columns, share_columns
+
         res = HotPathResult()
-        dev = self.device
+        dev, world, rank = self.device, self.world, self.rank
         n, N, b = self.n, self.N, opt.log_blowup
+        c = self.ctx = base.ctx
+        nb, C = L.num_base_columns, L.num_columns
+        row_lo, row_cnt = rank * (N // world), N // world
+        handles = []
         self.mark("start")
+        # one matrix for every committed column: trace | composition (ce) | w | u | v  (see __init__)
+        all_lde = torch.empty((C + self.ce + 3, N, 4), dtype=torch.int64, device=dev)
+        lde = all_lde[:C]
+        coeffs = torch.empty((C, n, 4), dtype=torch.int64, device=dev)      # only the owned columns are filled
+
+        def lde_cols(src: Matrix, first_col: int):
+            for j in owned_columns(src.num_cols, rank, world):
+                c.check(c.lib.ss_lde(c.handle, _lib.FIELD_FP252, ctypes.c_void_p(src.data[j].data_ptr()), n, 1, self.log_n, b,
+                                     ctypes.c_void_p(lde[first_col + j].data_ptr()), N, ctypes.c_void_p(coeffs[first_col + j].data_ptr()), n,
+                                     _lib.ORDER_NATURAL, None))
+
         # 3-5: base trace
-        # one matrix for every committed column: trace columns first, the ce composition columns last
-        # (the DEEP stage reads all of them; a single allocation avoids a 50 GB concatenation at 2^22 steps)
-        all_lde = torch.empty((L.num_columns + self.ce + 3, N, 4), dtype=torch.int64, device=dev)
-        lde = all_lde[: L.num_columns]
-        coeffs = torch.empty((L.num_columns, n, 4), dtype=torch.int64, device=dev)
-        c = base.ctx
-        nb = L.num_base_columns
-
-        def lde_into(src: Matrix, first_col: int):
-            c.check(c.lib.ss_lde(c.handle, _lib.FIELD_FP252, ctypes.c_void_p(src.data.data_ptr()), n, src.num_cols, self.log_n, b,
-                                 ctypes.c_void_p(lde[first_col].data_ptr()), N, ctypes.c_void_p(coeffs[first_col].data_ptr()), n,
-                                 _lib.ORDER_NATURAL, None))
-
-        lde_into(base, 0)
+        lde_cols(base, 0)
         self.mark("lde_base")
-        base_tree = MatrixMerkleTree.from_matrix(Matrix(lde[:nb], c), opt.tree_kind)
+        share_columns(lde[:nb], world)
+        self.mark("share_base")
+        res.roots["base"], h = self._commit(lde.data_ptr(), N, nb, self.log_n + b); handles.append(h)
         self.mark("merkle_base")
         # 8: extension trace
-        lde_into(ext, nb)
+        lde_cols(ext, nb)
         self.mark("lde_ext")
-        ext_tree = MatrixMerkleTree.from_matrix(Matrix(lde[nb:], c), opt.tree_kind)
+        share_columns(lde[nb:], world)
+        self.mark("share_ext")
+        res.roots["ext"], h = self._commit(lde[nb].data_ptr(), N, C - nb, self.log_n + b); handles.append(h)
         self.mark("merkle_ext")
-        # 9: constraint evaluation
+        # 9: constraint evaluation (row range of this rank), boundary denominators from w = 1/(x - 1)
         prog = self.composition_program()
         inv_x_minus_c(all_lde[self.w_col], _mont(1), c)
-        comp_evals = evaluate(prog, Matrix(all_lde, c), b)
+        comp_evals = torch.empty((N, 4), dtype=torch.int64, device=dev)
+        evaluate(prog, Matrix(all_lde, c), b, out=comp_evals, rows=(row_lo, row_cnt) if world > 1 else None)
+        self._gather_rows(comp_evals, row_lo, row_cnt)
         self.mark("constraint_eval")
         # 10: composition polynomial -> ce columns (coefficients j, j+ce, ...) -> LDE -> commit
         work = Matrix(comp_evals.view(1, N, 4), c)
@@ -144,21 +190,32 @@ class HotPathProver:
         comp_lde.zero_()
         comp_lde[:, :n] = comp_coeffs
         self.mark("comp_split")
-        comp_lde_m = Matrix(comp_lde, c).ntt_(coset=True)
+        Matrix(comp_lde, c).ntt_(coset=True)
         self.mark("ntt_comp_fwd")
-        comp_tree = MatrixMerkleTree.from_matrix(comp_lde_m, opt.tree_kind)
+        res.roots["composition"], h = self._commit(comp_lde.data_ptr(), N, self.ce, self.log_n + b); handles.append(h)
         self.mark("merkle_comp")
-        res.roots = {"base": base_tree.root(), "ext": ext_tree.root(), "composition": comp_tree.root()}
-        # 11: out-of-domain evaluations
+        # 11: out-of-domain evaluations (each rank evaluates the taps of the columns whose coefficients it holds)
         z = self._draw()
         taps = L.taps()
         pts = [z * pow(self.g, off, P) % P for _, off in taps]
-        ood = poly_eval(Matrix(coeffs, c), [col for col, _ in taps], np.stack([_mont(p) for p in pts]))
+
+        def owner(col):
+            return (col % world) if col < nb else ((col - nb) % world)
+
+        mine = [k for k, (col, _) in enumerate(taps) if owner(col) == rank]
+        ood = torch.zeros((len(taps), 4), dtype=torch.int64, device=dev)
+        if mine:
+            vals = poly_eval(Matrix(coeffs, c), [taps[k][0] for k in mine], np.stack([_mont(pts[k]) for k in mine]))
+            ood[torch.tensor(mine, device=dev)] = torch.from_numpy(vals.view(np.int64)).to(dev)
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(ood)                  # exactly one rank contributes each row, the others add zeros
         zc = pow(z, self.ce, P)
         ood_c = poly_eval(Matrix(comp_coeffs, c), list(range(self.ce)), np.stack([_mont(zc)] * self.ce), natural_order=True)
         self.mark("ood")
         from_m = lambda a: [(int(r[0]) | int(r[1]) << 64 | int(r[2]) << 128 | int(r[3]) << 192) * pow(R, -1, P) % P for r in a]
-        res.ood_trace, res.ood_composition = from_m(ood), from_m(ood_c)
+        res.ood_trace, res.ood_composition = from_m(ood.cpu().numpy().view(np.uint64)), from_m(ood_c)
         # 12: DEEP composition over the LDE coset (coefficients = powers of one alpha, src/lib.rs:102-116)
         alpha = self._draw()
         t_terms, c_terms, k = [], [], 0
@@ -170,34 +227,42 @@ class HotPathProver:
         inv_x_minus_c(all_lde[self.v_col], _mont(zc), c)
         deep_prog = compile_program(deep_expr_shifted(t_terms, c_terms, self.u_col, self.v_col, self.g, P), self.log_n, b)
         del coeffs, comp_coeffs, comp_evals, work
-        deep = evaluate(deep_prog, Matrix(all_lde, c), b)
+        deep = torch.empty((N, 4), dtype=torch.int64, device=dev)
+        evaluate(deep_prog, Matrix(all_lde, c), b, out=deep, rows=(row_lo, row_cnt) if world > 1 else None)
+        self._gather_rows(deep, row_lo, row_cnt)
         self.mark("deep")
         # 13: FRI layers
         evals, log_size, offset = deep, self.log_n + b, 3
         layers = []
         while (1 << log_size) >> b > opt.max_remainder_coeffs and log_size > opt.log_fold:
             rows = 1 << (log_size - opt.log_fold)
-            handle = ctypes.c_void_p()
             # the layer matrix (rows x fold) is the evaluation buffer viewed with col_stride = rows
-            c.check(c.lib.ss_merkle_build(c.handle, opt.tree_kind, 0, ctypes.c_void_p(evals.data_ptr()), rows, 1 << opt.log_fold,
-                                          log_size - opt.log_fold, _lib.ORDER_NATURAL, ctypes.byref(handle), None))
-            root = (ctypes.c_uint8 * 32)()
-            c.check(c.lib.ss_merkle_root(c.handle, handle, root))
-            res.fri_roots.append(bytes(root))
+            root, handle = self._commit(evals.data_ptr(), rows, 1 << opt.log_fold, log_size - opt.log_fold)
+            res.fri_roots.append(root)
             fri_alpha = self._draw()
-            nxt = fri_fold(evals, opt.log_fold, _mont(fri_alpha), _mont(offset), ctx=c)
+            shard = world > 1 and rows >= (1 << 16)
+            lo, cnt = (rank * (rows // world), rows // world) if shard else (0, 0)
+            nxt = fri_fold(evals, opt.log_fold, _mont(fri_alpha), _mont(offset), ctx=c, rows=(lo, cnt) if shard else None)
+            if shard:
+                self._gather_rows(nxt, lo, cnt)
             layers.append((handle, evals, log_size))
             evals, log_size, offset = nxt, log_size - opt.log_fold, pow(offset, 1 << opt.log_fold, P)
         res.remainder = evals.cpu().numpy().view(np.uint64)
         self.final_domain = (log_size, offset)
         self.mark("fri")
-        # 15: queries (positions from the seeded generator; openings + rows through the ABI)
-        if queries:
+        # 15: queries (positions from the seeded generator; openings + rows through the ABI) — single-GPU trees only
+        if queries and world == 1:
             pos = sorted({self.rnd.randrange(N) for _ in range(opt.num_queries)})
             res.query_positions = pos
-            for tree in (base_tree, ext_tree, comp_tree):
-                pr = tree.prove_rows(pos)
-                res.opened_bytes += pr["rows"].nbytes + pr["paths"].nbytes
+            idx = np.array(pos, dtype=np.uint64)
+            for h, (first, ncols) in zip(handles, ((0, nb), (nb, C - nb), (self.comp_col, self.ce))):
+                paths = np.zeros((len(idx), self.log_n + b, 32), dtype=np.uint8)
+                c.check(c.lib.ss_merkle_open(c.handle, h, idx.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), len(idx),
+                                             paths.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))))
+                rows_out = np.zeros((len(idx), ncols, 4), dtype=np.uint64)
+                c.check(c.lib.ss_rows_gather(c.handle, ctypes.c_void_p(all_lde[first].data_ptr()), N, ncols,
+                                             idx.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), len(idx), rows_out.ctypes.data_as(ctypes.c_void_p)))
+                res.opened_bytes += paths.nbytes + rows_out.nbytes
             for handle, layer_evals, ls in layers:
                 rows = 1 << (ls - opt.log_fold)
                 idx = np.array(sorted({p % rows for p in pos}), dtype=np.uint64)
@@ -209,6 +274,8 @@ class HotPathProver:
             self.mark("queries")
         for handle, _, _ in layers:
             c.lib.ss_tree_free(handle)
+        for h in handles:
+            c.lib.ss_tree_free(h)
         return res
 
     def stage_ms(self) -> dict:

@@ -72,10 +72,10 @@ def test_rejects_malformed_programs(ss, oracle):
     c = ss.default_context()
     bad = bytearray(prog.blob)
     bad[0] ^= 0xFF
-    assert c.lib.ss_constraint_eval(c.handle, bytes(bad), len(bad), ctypes.c_void_p(d.data_ptr()), 16, 1, 3, 1, ctypes.c_void_p(out.data_ptr()), None) == -1
+    assert c.lib.ss_constraint_eval(c.handle, bytes(bad), len(bad), ctypes.c_void_p(d.data_ptr()), 16, 1, 3, 1, 0, 0, ctypes.c_void_p(out.data_ptr()), None) == -1
     # wrong size / wrong log_n
-    assert c.lib.ss_constraint_eval(c.handle, prog.blob, len(prog.blob) - 32, ctypes.c_void_p(d.data_ptr()), 16, 1, 3, 1, ctypes.c_void_p(out.data_ptr()), None) == -1
-    assert c.lib.ss_constraint_eval(c.handle, prog.blob, len(prog.blob), ctypes.c_void_p(d.data_ptr()), 32, 1, 4, 1, ctypes.c_void_p(out.data_ptr()), None) == -1
+    assert c.lib.ss_constraint_eval(c.handle, prog.blob, len(prog.blob) - 32, ctypes.c_void_p(d.data_ptr()), 16, 1, 3, 1, 0, 0, ctypes.c_void_p(out.data_ptr()), None) == -1
+    assert c.lib.ss_constraint_eval(c.handle, prog.blob, len(prog.blob), ctypes.c_void_p(d.data_ptr()), 32, 1, 4, 1, 0, 0, ctypes.c_void_p(out.data_ptr()), None) == -1
 
 
 def test_deep_composition_matches_definition(ss, oracle):
