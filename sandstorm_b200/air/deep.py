@@ -33,21 +33,36 @@ def deep_expr_shifted(trace_terms, comp_terms, u_col: int, v_col: int, g: int, p
         u[i] = 1 / (x_i - z)      (column u_col)        v[i] = 1 / (x_i - z^ce)     (column v_col)
         1 / (x_i - z g^off) = g^-off * u[i - blowup * off]            (x_i - z g^off = g^off (x_{i - b off} - z))
 
+    and regrouped BY COLUMN so that almost every multiplication has a constant operand and lands in an
+    unreduced dot product (program.py DOT; one Montgomery reduction per column instead of one per term):
+
+        sum_t a_t (T_c(x) - y_t) / (x - z g^off_t)
+            = sum_c T_c(x) * [ sum_{t in c} a_t g^-off_t u[i - b off_t] ]  -  sum_off K_off u[i - b off],
+        K_off = g^-off * sum_{t at off} a_t y_t.
+
     trace_terms: (column, offset, claimed value y, coefficient);  comp_terms: (column, y, coefficient).
     `Trace(u_col, -off)` is a row offset in TRACE units, i.e. -off * blowup LDE rows, exactly the shift above."""
-    by_off: dict[int, Expr] = {}
+    per_col: dict[int, Expr] = {}
+    k_off: dict[int, int] = {}
     for col, off, y, coeff in trace_terms:
-        term = Constant(coeff) * (Trace(col, 0) - Constant(y))
-        by_off[off] = term if off not in by_off else by_off[off] + term
+        gi = pow(g, -off, p)
+        term = Constant(coeff * gi % p) * Trace(u_col, -off)
+        per_col[col] = term if col not in per_col else per_col[col] + term
+        k_off[off] = (k_off.get(off, 0) + coeff * y % p * gi) % p
     total = None
-    for off, num in by_off.items():
-        q = num * Constant(pow(g, -off, p)) * Trace(u_col, -off)
+    for col, a in per_col.items():
+        q = Trace(col, 0) * a
         total = q if total is None else total + q
-    comp = None
+    for off, k in k_off.items():
+        if k:
+            q = Constant(k) * Trace(u_col, -off)
+            total = -q if total is None else total - q
+    comp, comp_y = None, 0
     for col, y, coeff in comp_terms:
-        term = Constant(coeff) * (Trace(col, 0) - Constant(y))
+        term = Constant(coeff) * Trace(col, 0)
         comp = term if comp is None else comp + term
+        comp_y = (comp_y + coeff * y) % p
     if comp is not None:
-        q = comp * Trace(v_col, 0)
+        q = (comp - Constant(comp_y)) * Trace(v_col, 0)
         total = q if total is None else total + q
     return total

@@ -5,18 +5,30 @@ evaluator) is split here between host and device:
 
   host   : substitute challenges / hints / composition coefficient, fold constants, hash-cons (CSE),
            classify every node by its PERIOD in the LDE row index i (x_i = 3 * w_N^i):
-             period 1        -> constant
+             period 1         -> constant
              period T <= 2^17 -> lookup table of T entries (zerofiers X^(n/k) - c and their inverses,
-                                periodic columns P(X^(n/interval)), products of those)
-             full            -> depends on trace cells or on X itself -> device instruction
-           full-period denominators (the X - g^e boundary terms) are inverted together per row with
-           one batched inversion.
-  device : one thread per LDE row runs the instruction list over a small slot file (liveness-allocated).
+                                 periodic columns P(X^(n/interval)), products of those)
+             full             -> depends on trace cells or on X itself -> device instruction
+           then rewrite the full-period part as LINEAR COMBINATIONS over non-linear atoms:
+             * constant factors are folded into coefficients at compile time;
+             * the root sum  sum_i alpha^i * num_i * D_i  is regrouped by shared factors D (zerofier
+               tables, boundary-denominator taps):  sum_D D * (sum_{i in D} alpha^i * num_i);
+             * a linear combination with general coefficients becomes one DOT instruction: the products
+               are accumulated unreduced (512 bits) and Montgomery-reduced once;
+             * every value carries an exact upper bound, so additions are raw, subtractions add a
+               pre-computed multiple of p, and a reduction (RED) is emitted only where a bound would
+               overflow 2^256 — the device never compares magnitudes.
+  device : one thread per LDE row runs the instruction list over a small slot file (liveness-allocated);
+           constants, table entries and trace taps are fetched directly as instruction operands.
 
-Program blob layout (little-endian u32 words unless noted):
-  [0] magic 'SSCP'  [1] version  [2] n_instr  [3] n_consts  [4] n_tables  [5] n_slots  [6] log_n (trace)
-  [7] log_blowup    then n_tables x (log_period, offset in elements), padded to an even count
-  then n_instr x 4 words (op | dst << 8, a, b, imm)    then consts (32 B each)   then table data (32 B each)
+Program blob, version 2 (little-endian u32 words unless noted):
+  [0] magic 'SSCP'  [1] version  [2] n_words (16-byte code words)  [3] n_consts  [4] n_tables  [5] n_slots
+  [6] log_n (trace) [7] log_blowup  [8] n_taps  [9..15] reserved
+  then n_tables x (log_period, offset in elements), padded to an even count
+  then n_taps x (column, row offset mod N in LDE rows), padded to an even count
+  then n_words x 4 words of code     then consts (32 B each)   then table data (32 B each)
+Code word:  (op | dst << 8 | n << 16, A, B, 0);  a DOT is followed by ceil(n / 2) words (A0, B0, A1, B1).
+Operand word:  kind << 29 | payload   kind 0 slot | 1 const index | 2 tap index | 3 table index | 4 x_i.
 """
 from __future__ import annotations
 
@@ -30,11 +42,12 @@ from .expr import Expr, P
 
 R = 2**256
 MAGIC = 0x50435353          # 'SSCP'
-VERSION = 1
+VERSION = 2
 MAX_TABLE_LOG = 17
 GENERATOR = 3
 
-OP_NOP, OP_CONST, OP_TRACE, OP_TABLE, OP_X, OP_ADD, OP_SUB, OP_MUL, OP_NEG, OP_INV, OP_BATCHINV, OP_OUT, OP_MULC, OP_ADDC = range(14)
+OP_NOP, OP_MOV, OP_ADD, OP_SUBK, OP_RED, OP_MUL, OP_DOT, OP_INV, OP_OUT = range(9)
+K_SLOT, K_CONST, K_TAP, K_TABLE, K_X = range(5)
 FULL = 0    # period marker for row-dependent nodes
 
 
@@ -55,6 +68,9 @@ class CompiledProgram:
     n_trace_taps: int
     n_batch_inv: int
     table_sizes: list = field(default_factory=list)
+    n_red: int = 0
+    n_dot: int = 0
+    n_inv: int = 0
 
 
 class _Lower:
@@ -176,17 +192,129 @@ class _Lower:
         self.memo_eval[key] = v
         return v
 
+    # -- 4. all values of a periodic node over one period (rows 0 .. period-1), vectorised over the rows ----------
+    def table_values(self, e: Expr, memo: dict | None = None) -> list:
+        memo = {} if memo is None else memo
+        hit = memo.get(e)
+        if hit is not None:
+            return hit
+        op = e.op
+        T = self.period(e)
+        assert T != FULL
+
+        def powers(k: int, count: int) -> list:
+            """(3 * w^j)^k for j < count."""
+            step, v, out = pow(self.w, k % self.N, P), pow(GENERATOR, k, P), []
+            for _ in range(count):
+                out.append(v)
+                v = v * step % P
+            return out
+
+        if op == "const":
+            vals = [e.args[0] % P]
+        elif op == "pow":
+            vals = powers(e.args[1], T)
+        elif op == "x":
+            vals = powers(1, T)
+        elif op == "periodic":
+            coeffs, interval = e.args
+            ys = powers(self.n // interval, T)
+            vals = [0] * T
+            for c in reversed(coeffs):
+                vals = [(v * y + c) % P for v, y in zip(vals, ys)]
+        else:
+            args = [self.table_values(a, memo) for a in e.args]
+            a = args[0]
+            if len(a) != T:
+                a = a * (T // len(a))
+            if len(args) > 1:
+                b = args[1]
+                if len(b) != T:
+                    b = b * (T // len(b))
+            if op == "add": vals = [(x + y) % P for x, y in zip(a, b)]
+            elif op == "sub": vals = [(x - y) % P for x, y in zip(a, b)]
+            elif op == "mul": vals = [x * y % P for x, y in zip(a, b)]
+            elif op == "neg": vals = [-x % P for x in a]
+            elif op == "div":
+                # Montgomery's trick: one modular inversion per table
+                pre, acc = [], 1
+                for y in b:
+                    if y == 0:
+                        raise ZeroDivisionError("periodic denominator vanishes on the LDE coset")
+                    pre.append(acc)
+                    acc = acc * y % P
+                inv = pow(acc, -1, P)
+                invs = [0] * T
+                for j in range(T - 1, -1, -1):
+                    invs[j] = inv * pre[j] % P
+                    inv = inv * b[j] % P
+                vals = [x * y % P for x, y in zip(a, invs)]
+            else:
+                raise ValueError(op)
+        memo[e] = vals
+        return vals
+
+
+LIM = 1 << 256                       # every stored value must stay below this
+RED_BOUND = 1 << 252                 # bound after RED
+OUT_CAP = 8 * P                      # products are kept below this so that sums of a few of them still fit
+ACC_LIM = (1 << 512) - P * R         # an unreduced accumulator (plus the p * 2^256 bias) must fit 512 bits
+ACC_SOFT = 7 * P * R                 # ... and its reduction should come out below OUT_CAP
+DOT_SLOT_CHUNK = 8                   # slot operands alive at once inside one DOT
+DOT_MAX_TERMS = 4096
+
+
+def _mul_bound(ba: int, bb: int) -> int:
+    """exclusive upper bound of fp::mul / acc_reduce for operands below ba, bb (fp252.cuh: result <= a*b/R + p)."""
+    return ba * bb // R + P + 1
+
+
+class _Graph:
+    """Hash-consed device DAG.  kinds: const(v) table(tid) x trace(col, off_lde) mul(a, b) inv(a) lc(((node, coeff), ...), c0)"""
+
+    def __init__(self):
+        self.kind: list[str] = []
+        self.args: list[tuple] = []
+        self.index: dict = {}
+
+    def mk(self, kind: str, *args) -> int:
+        key = (kind,) + args
+        hit = self.index.get(key)
+        if hit is None:
+            hit = len(self.kind)
+            self.kind.append(kind)
+            self.args.append(args)
+            self.index[key] = hit
+        return hit
+
+    def children(self, nid: int):
+        k, a = self.kind[nid], self.args[nid]
+        if k == "mul":
+            return list(a)
+        if k == "inv":
+            return [a[0]]
+        if k == "lc":
+            return [t for t, _ in a[0]]
+        return []
+
+
+LEAF_KINDS = ("const", "table", "trace")
+
 
 def compile_program(expr: Expr, log_n: int, log_blowup: int, challenges=(), hints=(), composition_coeffs=(0,),
-                    max_slots: int = 256) -> CompiledProgram:
+                    max_slots: int = 256, regroup: bool = True) -> CompiledProgram:
     """expr: the composition constraint (or any Expr).  challenges / hints / composition_coeffs: canonical ints."""
+    import sys
+    sys.setrecursionlimit(max(sys.getrecursionlimit(), 200000))
     lw = _Lower(log_n, log_blowup, list(challenges), list(hints), list(composition_coeffs))
     root = lw.norm(expr)
-    N = lw.N
+    g = _Graph()
 
     consts: list[int] = []
     const_ix: dict[int, int] = {}
-    tables: list[list[int]] = []
+    tap_list: list[tuple] = []           # distinct (column, row offset mod N)
+    tap_ix: dict[tuple, int] = {}
+    tables: list = []                    # Expr per table (values are produced at serialisation time)
     table_ix: dict[Expr, int] = {}
 
     def const_id(v: int) -> int:
@@ -196,79 +324,234 @@ def compile_program(expr: Expr, log_n: int, log_blowup: int, challenges=(), hint
             consts.append(v)
         return const_ix[v]
 
-    def table_id(e: Expr) -> int:
+    def table_node(e: Expr) -> int:
         if e not in table_ix:
-            T = lw.period(e)
             table_ix[e] = len(tables)
-            tables.append([lw.eval_at(e, j) for j in range(T)])
-            lw.memo_eval.clear()
-        return table_ix[e]
+            tables.append(e)
+        return g.mk("table", table_ix[e])
 
-    # ---- lower the full-period part into a DAG of device nodes (hash-consed tuples) -----------------------
-    dev_memo: dict[Expr, tuple] = {}
-    inv_nodes: list[tuple] = []          # ('inv', denominator_node) for full-period denominators
+    # ---- 1. linear combinations over atoms ---------------------------------------------------------------
+    def node_of(lc) -> int:
+        terms, c0 = lc
+        if not terms:
+            return g.mk("const", c0 % P)
+        if len(terms) == 1 and c0 == 0:
+            (nid, c), = terms.items()
+            if c == 1:
+                return nid
+        return g.mk("lc", tuple(sorted(terms.items())), c0 % P)
 
-    def lower(e: Expr) -> tuple:
-        hit = dev_memo.get(e)
+    def lc_add(a, b, sign=1):
+        terms = dict(a[0])
+        for k, v in b[0].items():
+            nv = (terms.get(k, 0) + sign * v) % P
+            if nv:
+                terms[k] = nv
+            else:
+                terms.pop(k, None)
+        return terms, (a[1] + sign * b[1]) % P
+
+    def lc_scale(a, c):
+        c %= P
+        if c == 0:
+            return {}, 0
+        if c == 1:
+            return a
+        terms, c0 = a
+        if c == P - 1 or len(terms) <= 1 or all(v not in (1, P - 1) for v in terms.values()):
+            return {k: v * c % P for k, v in terms.items()}, c0 * c % P
+        return {node_of(a): c}, 0
+
+    def lc_split(a):
+        """(coefficient, node) with a == coefficient * node."""
+        terms, c0 = a
+        if len(terms) == 1 and c0 == 0:
+            (nid, c), = terms.items()
+            return c, nid
+        return 1, node_of(a)
+
+    def lc_mul(a, b):
+        if not a[0]:
+            return lc_scale(b, a[1])
+        if not b[0]:
+            return lc_scale(a, b[1])
+        ca, na = lc_split(a)
+        cb, nb = lc_split(b)
+        return {g.mk("mul", min(na, nb), max(na, nb)): ca * cb % P}, 0
+
+    memo_lc: dict[Expr, tuple] = {}
+    ONE = Expr("const", 1)
+
+    def lower(e: Expr):
+        hit = memo_lc.get(e)
         if hit is not None:
             return hit
         p = lw.period(e)
         if p == 1:
-            node = ("const", const_id(lw.eval_at(e, 0)))
+            r = ({}, lw.eval_at(e, 0) % P)
         elif p != FULL:
-            node = ("table", table_id(e))
+            r = ({table_node(e): 1}, 0)
         elif e.op == "x":
-            node = ("x",)
+            r = ({g.mk("x"): 1}, 0)
         elif e.op == "trace":
-            node = ("trace", e.args[0], e.args[1] * (1 << log_blowup))
+            r = ({g.mk("trace", e.args[0], e.args[1] * (1 << log_blowup)): 1}, 0)
         elif e.op == "pow":                                      # X^k with a long period: square-and-multiply on X
-            k, acc, sq = e.args[1], None, ("x",)
+            k, acc, sq = e.args[1], None, ({g.mk("x"): 1}, 0)
             while k:
                 if k & 1:
-                    acc = sq if acc is None else ("mul", acc, sq)
+                    acc = sq if acc is None else lc_mul(acc, sq)
                 k >>= 1
                 if k:
-                    sq = ("mul", sq, sq)
-            node = acc
+                    sq = lc_mul(sq, sq)
+            r = acc
         elif e.op == "periodic":
             raise ValueError("periodic column with a period above the table limit")
         elif e.op == "div":
             num, den = e.args
             if lw.period(den) != FULL:
-                node = ("mul", lower(num), lower(Expr("div", Expr("const", 1), den)))
+                r = lc_mul(lower(num), lower(Expr("div", ONE, den)))
             else:
-                inv = ("inv", lower(den))
-                if inv not in inv_nodes:
-                    inv_nodes.append(inv)
-                node = ("mul", lower(num), inv)
+                r = lc_mul(lower(num), ({g.mk("inv", node_of(lower(den))): 1}, 0))
         elif e.op == "neg":
-            node = ("neg", lower(e.args[0]))
+            r = lc_scale(lower(e.args[0]), P - 1)
+        elif e.op == "add":
+            r = lc_add(lower(e.args[0]), lower(e.args[1]))
+        elif e.op == "sub":
+            r = lc_add(lower(e.args[0]), lower(e.args[1]), -1)
+        elif e.op == "mul":
+            r = lc_mul(lower(e.args[0]), lower(e.args[1]))
         else:
-            node = (e.op, lower(e.args[0]), lower(e.args[1]))
-        dev_memo[e] = node
-        return node
-
-    import sys
-    sys.setrecursionlimit(max(sys.getrecursionlimit(), 100000))
-    root_node = lower(root)
-
-    # ---- schedule: denominators first (pinned contiguous slots), one BATCHINV, then the rest -----------
-    dep_memo: dict = {}
-
-    def depends_on_inv(node):
-        if node in dep_memo:
-            return dep_memo[node]
-        r = node[0] == "inv" or any(isinstance(c, tuple) and depends_on_inv(c) for c in node[1:])
-        dep_memo[node] = r
+            raise ValueError(e.op)
+        memo_lc[e] = r
         return r
 
-    batch = [iv for iv in inv_nodes if not depends_on_inv(iv[1])][:192]
-    batch_set = set(batch)
+    root_lc = lower(root)
+
+    # ---- 2. regroup the root sum by shared factors -----------------------------------------------------------
+    def flatten(nid: int) -> list[int]:
+        if g.kind[nid] == "mul":
+            return flatten(g.args[nid][0]) + flatten(g.args[nid][1])
+        return [nid]
+
+    def product(ids: list[int]) -> int:
+        """one node for the product of `ids`: periodic factors are merged into a single table first."""
+        tabs = [i for i in ids if g.kind[i] == "table"]
+        rest = sorted(i for i in ids if g.kind[i] != "table")
+        if len(tabs) > 1:
+            e = tables[g.args[tabs[0]][0]]
+            for t in tabs[1:]:
+                e = Expr("mul", e, tables[g.args[t][0]])
+            tabs = [table_node(e)]
+        acc = None
+        for i in tabs + rest:
+            acc = i if acc is None else g.mk("mul", min(acc, i), max(acc, i))
+        return acc
+
+    if regroup and len(root_lc[0]) > 1:
+        facs = {nid: flatten(nid) for nid in root_lc[0]}
+        usage: dict[int, int] = {}
+        for fl in facs.values():
+            for f in set(fl):
+                usage[f] = usage.get(f, 0) + 1
+        groups: dict[tuple, list] = {}
+        new_terms: dict[int, int] = {}
+
+        def add_term(nid, c):
+            nv = (new_terms.get(nid, 0) + c) % P
+            if nv:
+                new_terms[nid] = nv
+            else:
+                new_terms.pop(nid, None)
+
+        for nid, c in root_lc[0].items():
+            fl = facs[nid]
+            shared = [f for f in fl if g.kind[f] in ("table", "inv") or usage[f] > 1]
+            own = [f for f in fl if not (g.kind[f] in ("table", "inv") or usage[f] > 1)]
+            if not own:                                       # everything is shared: keep the least shared factor as the numerator
+                k = min(range(len(shared)), key=lambda j: (usage[shared[j]], g.kind[shared[j]] in LEAF_KINDS))
+                own, shared = [shared[k]], shared[:k] + shared[k + 1:]
+            if not shared:
+                add_term(nid, c)
+                continue
+            groups.setdefault(tuple(sorted(shared)), []).append((product(own), c))
+        for key, members in groups.items():
+            key = list(key)
+            inner: dict[int, int] = {}
+            for nid, c in members:
+                nv = (inner.get(nid, 0) + c) % P
+                if nv:
+                    inner[nid] = nv
+                else:
+                    inner.pop(nid, None)
+            if not inner:
+                continue
+            if len(inner) == 1:
+                (nid, c), = inner.items()
+                tabs = [f for f in key if g.kind[f] == "table"]
+                if c != 1 and tabs:                            # fold the coefficient into the table
+                    e = Expr("mul", Expr("const", c), tables[g.args[tabs[0]][0]])
+                    key[key.index(tabs[0])] = table_node(e)
+                    add_term(product([nid] + key), 1)
+                elif c != 1:
+                    add_term(product([nid] + key), c)
+                else:
+                    add_term(product([nid] + key), 1)
+            else:
+                add_term(product([node_of((inner, 0))] + key), 1)
+        root_lc = (new_terms, root_lc[1])
+    root_node = node_of(root_lc)
+
+    # ---- 3. batched inversion of the independent full-period denominators (Montgomery's trick as DAG nodes) ---
+    reach: set[int] = set()
+    order: list[int] = []
+
+    def visit(nid):
+        if nid in reach:
+            return
+        reach.add(nid)
+        for ch in g.children(nid):
+            visit(ch)
+        order.append(nid)
+
+    visit(root_node)
+    has_inv: dict[int, bool] = {}
+    for nid in order:                                          # children before parents
+        has_inv[nid] = g.kind[nid] == "inv" or any(has_inv[ch] for ch in g.children(nid))
+    inv_nodes = [nid for nid in order if g.kind[nid] == "inv" and not has_inv[g.args[nid][0]]]
+    subst: dict[int, int] = {}
+    if len(inv_nodes) > 1:
+        dens = [g.args[nid][0] for nid in inv_nodes]
+        pre = [dens[0]]
+        for d in dens[1:]:
+            pre.append(g.mk("mul", min(pre[-1], d), max(pre[-1], d)))
+        run = g.mk("inv", pre[-1])
+        for k in range(len(dens) - 1, 0, -1):
+            subst[inv_nodes[k]] = g.mk("mul", min(run, pre[k - 1]), max(run, pre[k - 1]))
+            run = g.mk("mul", min(run, dens[k]), max(run, dens[k]))
+        subst[inv_nodes[0]] = run
+
+    def resolve(nid: int) -> int:
+        return subst.get(nid, nid)
+
+    # ---- 4. schedule: liveness-allocated slots, exact bounds, operand-fused three-address code ----------------
+    uses: dict[int, int] = {}
+
+    def count(nid):
+        nid = resolve(nid)
+        uses[nid] = uses.get(nid, 0) + 1
+        if uses[nid] == 1:
+            for ch in g.children(nid):
+                count(ch)
+
+    count(root_node)
+
     code: list[tuple] = []
-    slot_of: dict[tuple, int] = {}
+    slot_of: dict[int, int] = {}
+    bound: dict[int, int] = {}
     free: list[int] = []
     n_slots = 0
-    stats = {"mul": 0, "addsub": 0, "trace": 0}
+    stats = {"mul": 0, "addsub": 0, "trace": 0, "red": 0, "dot": 0, "inv": 0}
+    X_BOUND = _mul_bound(P, P)
 
     def alloc() -> int:
         nonlocal n_slots
@@ -277,129 +560,224 @@ def compile_program(expr: Expr, log_n: int, log_blowup: int, challenges=(), hint
         n_slots += 1
         return n_slots - 1
 
-    # use counts for liveness
-    uses: dict[tuple, int] = {}
+    class Opnd:
+        """an instruction operand: a leaf fetched in place, or a slot (owned by a node or temporary)."""
+        __slots__ = ("word", "slot", "nid")
 
-    def count(node):
-        for c in node[1:]:
-            if isinstance(c, tuple):
-                uses[c] = uses.get(c, 0) + 1
-                if uses[c] == 1:
-                    count(c)
+        def __init__(self, word, slot=None, nid=None):
+            self.word, self.slot, self.nid = word, slot, nid
 
-    roots = [iv[1] for iv in batch] + [root_node]
-    for r in roots:
-        uses[r] = uses.get(r, 0) + 1
-        if uses[r] == 1:
-            count(r)
-    for iv in batch:                       # the inverse itself is consumed by its users
-        pass
+        @property
+        def b(self) -> int:
+            return bound[self.slot] if self.slot is not None else P
 
-    pinned: set[int] = set()
+    def leaf_opnd(nid: int) -> Opnd:
+        k, a = g.kind[nid], g.args[nid]
+        if k == "const":
+            return Opnd(K_CONST << 29 | const_id(a[0]))
+        if k == "table":
+            return Opnd(K_TABLE << 29 | a[0])
+        col, off = a
+        key = (col, off % lw.N)
+        if key not in tap_ix:
+            tap_ix[key] = len(tap_list)
+            tap_list.append(key)
+        stats["trace"] += 1
+        return Opnd(K_TAP << 29 | tap_ix[key])
 
-    def release(node):
-        uses[node] -= 1
-        if node[0] in ("const", "table", "x", "trace"):
-            if leaf_slot:
-                free.append(leaf_slot.pop())        # the slot this use materialised
+    def operand(nid: int) -> Opnd:
+        nid = resolve(nid)
+        if g.kind[nid] in LEAF_KINDS:
+            return Opnd(leaf_opnd(nid).word, None, nid)
+        if nid not in slot_of:
+            emit(nid)
+        return Opnd(K_SLOT << 29 | slot_of[nid], slot_of[nid], nid)
+
+    def release(op: Opnd):
+        if op.nid is None:                                      # temporary
+            if op.slot is not None:
+                free.append(op.slot)
             return
-        if uses[node] == 0 and node in slot_of:
-            s = slot_of[node]
-            if s not in pinned:
-                free.append(s)
+        uses[op.nid] -= 1
+        if uses[op.nid] == 0 and op.nid in slot_of:
+            free.append(slot_of.pop(op.nid))
 
-    LEAVES = ("const", "table", "x", "trace")
+    def red(op: Opnd):
+        assert op.slot is not None
+        code.append((OP_RED | op.slot << 8, op.word, 0, 0))
+        bound[op.slot] = RED_BOUND
+        stats["red"] += 1
 
-    def emit(node) -> int:
-        # leaves are rematerialised at every use (a 32-byte L1/L2 hit is cheaper than a live slot):
-        # only interior nodes are kept alive across uses
-        if node in slot_of and node[0] not in LEAVES:
-            return slot_of[node]
-        kind = node[0]
-        if kind == "inv" and node in batch_set:
-            return slot_of[node]                                  # produced by BATCHINV
-        if kind == "const":
-            d = alloc(); code.append((OP_CONST, d, node[1], 0, 0))
-        elif kind == "table":
-            d = alloc(); code.append((OP_TABLE, d, node[1], 0, 0))
-        elif kind == "x":
-            d = alloc(); code.append((OP_X, d, 0, 0, 0))
-        elif kind == "trace":
-            d = alloc(); code.append((OP_TRACE, d, node[1], 0, node[2])); stats["trace"] += 1
-        elif kind == "neg":
-            a = emit(node[1]); release(node[1]); d = alloc(); code.append((OP_NEG, d, a, 0, 0)); stats["addsub"] += 1
-        elif kind == "inv":
-            a = emit(node[1]); release(node[1]); d = alloc(); code.append((OP_INV, d, a, 0, 0)); stats["mul"] += 262
-        else:
-            l, r = node[1], node[2]
-            # constant operand forms save a slot and an instruction
-            if kind == "mul" and (l[0] == "const" or r[0] == "const") and not (l[0] == "const" and r[0] == "const"):
-                c, o = (l, r) if l[0] == "const" else (r, l)
-                a = emit(o); release(o); uses[c] -= 1
-                d = alloc(); code.append((OP_MULC, d, a, c[1], 0)); stats["mul"] += 1
-            elif kind == "add" and (l[0] == "const" or r[0] == "const") and not (l[0] == "const" and r[0] == "const"):
-                c, o = (l, r) if l[0] == "const" else (r, l)
-                a = emit(o); release(o); uses[c] -= 1
-                d = alloc(); code.append((OP_ADDC, d, a, c[1], 0)); stats["addsub"] += 1
+    def reducible(op: Opnd) -> bool:
+        return op.slot is not None and bound[op.slot] > RED_BOUND
+
+    def put(opc: int, n: int, a: Opnd, b: Opnd | None, out_bound: int) -> Opnd:
+        """emit  tmp = op(a, b); the operands are released first so that the result may reuse one of their slots
+        (the device reads both operands completely before it writes the destination)."""
+        assert out_bound <= LIM, "bound analysis failed"
+        wa, wb = a.word, (b.word if b is not None else 0)
+        release(a)
+        if b is not None:
+            release(b)
+        d = alloc()
+        assert d < 256 and n < 65536
+        code.append((opc | d << 8 | n << 16, wa, wb, 0))
+        bound[d] = out_bound
+        return Opnd(K_SLOT << 29 | d, d, None)
+
+    def adopt(op: Opnd, nid: int):
+        """the temporary `op` becomes the value of node nid (copied first when it belongs to somebody else)."""
+        if op.nid is not None or op.slot is None:
+            op = put(OP_MOV, 0, op, None, op.b)
+        slot_of[nid] = op.slot
+
+    def pick_red(a: Opnd, b: Opnd) -> Opnd:
+        if reducible(a) and (a.b >= b.b or not reducible(b)):
+            return a
+        assert reducible(b), "bound analysis failed"
+        return b
+
+    def do_add(a: Opnd, b: Opnd) -> Opnd:
+        while a.b + b.b > LIM:
+            red(pick_red(a, b))
+        stats["addsub"] += 1
+        return put(OP_ADD, 0, a, b, a.b + b.b)
+
+    def do_sub(a: Opnd, b: Opnd) -> Opnd:
+        while True:
+            k = -(-b.b // P)
+            if k <= 31 and a.b + k * P <= LIM:
+                break
+            if reducible(b) and (k > 2 or not reducible(a)):
+                red(b)
             else:
-                # evaluate the deeper operand first (shorter live ranges)
-                a = emit(l); b = emit(r)
-                release(l); release(r)
-                d = alloc()
-                code.append(({"add": OP_ADD, "sub": OP_SUB, "mul": OP_MUL}[kind], d, a, b, 0))
-                stats["mul" if kind == "mul" else "addsub"] += 1
-        if kind in LEAVES:
-            leaf_slot.append(d)
+                assert reducible(a), "bound analysis failed (sub)"
+                red(a)
+        stats["addsub"] += 1
+        return put(OP_SUBK, k, a, b, a.b + k * P)
+
+    def do_mul(a: Opnd, b: Opnd) -> Opnd:
+        while _mul_bound(a.b, b.b) > OUT_CAP and (reducible(a) or reducible(b)):
+            red(pick_red(a, b))
+        assert a.b * b.b <= ACC_LIM
+        stats["mul"] += 1
+        return put(OP_MUL, 0, a, b, _mul_bound(a.b, b.b))
+
+    def do_dot(pairs: list) -> Opnd:
+        """pairs: [(Opnd, Opnd)]; the caller keeps the sum of bound products within ACC_SOFT."""
+        total = sum(a.b * b.b for a, b in pairs)
+        assert total <= ACC_LIM and 0 < len(pairs) < 65536
+        if len(pairs) == 1:
+            return do_mul(pairs[0][0], pairs[0][1])
+        words = [w for a, b in pairs for w in (a.word, b.word)]
+        if len(pairs) & 1:
+            words += [0, 0]
+        for a, b in pairs:
+            release(a)
+            release(b)
+        d = alloc()
+        assert d < 256
+        code.append((OP_DOT | d << 8 | len(pairs) << 16, 0, 0, 0))
+        for k in range(0, len(words), 4):
+            code.append(tuple(words[k:k + 4]))
+        bound[d] = _mul_bound(1, total)
+        assert bound[d] <= LIM
+        stats["mul"] += len(pairs)
+        stats["dot"] += 1
+        return Opnd(K_SLOT << 29 | d, d, None)
+
+    def const_opnd(v: int) -> Opnd:
+        return Opnd(K_CONST << 29 | const_id(v))
+
+    def emit_lc(nid: int):
+        terms, c0 = g.args[nid]
+        gen = [(t, c) for t, c in terms if c not in (1, P - 1)]
+        plus = [t for t, c in terms if c == 1]
+        minus = [t for t, c in terms if c == P - 1]
+        gen.sort(key=lambda tc: g.kind[resolve(tc[0])] in LEAF_KINDS)     # slot operands first, leaves fill the chunks up
+        acc: Opnd | None = None
+        chunk: list = []
+        chunk_total = chunk_slots = 0
+        for t, c in gen:
+            a = operand(t)
+            if reducible(a) and a.b > 8 * P:
+                red(a)
+            w = a.b * P
+            if chunk and (chunk_total + w > ACC_SOFT or (a.slot is not None and chunk_slots >= DOT_SLOT_CHUNK) or len(chunk) >= DOT_MAX_TERMS):
+                part = do_dot(chunk)
+                acc = part if acc is None else do_add(acc, part)
+                chunk, chunk_total, chunk_slots = [], 0, 0
+            chunk.append((a, const_opnd(c)))
+            chunk_total += w
+            chunk_slots += a.slot is not None
+        if chunk:
+            part = do_dot(chunk)
+            acc = part if acc is None else do_add(acc, part)
+        if c0:
+            acc = const_opnd(c0) if acc is None else do_add(acc, const_opnd(c0))
+        for t in plus:
+            op = operand(t)
+            acc = op if acc is None else do_add(acc, op)
+        for t in minus:
+            op = operand(t)
+            acc = do_sub(acc if acc is not None else const_opnd(0), op)
+        adopt(acc, nid)
+
+    def emit(nid: int):
+        k, a = g.kind[nid], g.args[nid]
+        if k == "x":
+            d = alloc()
+            code.append((OP_MOV | d << 8, K_X << 29, 0, 0))
+            bound[d] = X_BOUND
+            slot_of[nid] = d
+            stats["mul"] += 1
+        elif k == "mul":
+            x = operand(a[0])
+            y = operand(a[1])
+            adopt(do_mul(x, y), nid)
+        elif k == "inv":
+            x = operand(a[0])
+            if reducible(x) and x.b > OUT_CAP:
+                red(x)
+            adopt(put(OP_INV, 0, x, None, _mul_bound(OUT_CAP, OUT_CAP)), nid)
+            stats["mul"] += 262
+            stats["inv"] += 1
+        elif k == "lc":
+            emit_lc(nid)
         else:
-            slot_of[node] = d
-        return d
+            raise ValueError(k)
 
-    leaf_slot: list[int] = []
-
-    def emit_operand(node) -> int:
-        return emit(node)
-
-    if batch:
-        base = n_slots
-        for k, iv in enumerate(batch):     # reserve contiguous pinned slots [base, base + len)
-            n_slots += 1
-            pinned.add(base + k)
-        for k, iv in enumerate(batch):
-            den = iv[1]
-            s = emit(den)
-            # move into the pinned slot (ADDC 0); the denominator's own slot is recycled at once — if it
-            # is also used as a plain factor later it is recomputed (one subtraction)
-            code.append((OP_ADDC, base + k, s, const_id(0), 0))
-            if den[0] in LEAVES:
-                release(den)
-            else:
-                uses[den] -= 1
-                if s not in pinned:
-                    free.append(s)
-                slot_of.pop(den, None)
-            slot_of[iv] = base + k
-        code.append((OP_BATCHINV, 0, base, len(batch), 0))
-        stats["mul"] += 262 + 3 * (len(batch) - 1)
-    out_slot = emit(root_node)
-    code.append((OP_OUT, 0, out_slot, 0, 0))
+    out = operand(root_node)
+    if out.b > 4 * P:
+        red(out)
+    code.append((OP_OUT, out.word, 0, 0))
     if n_slots > max_slots:
         raise ValueError(f"program needs {n_slots} value slots, the kernel has {max_slots}")
 
-    # ---- serialise ------------------------------------------------------------------------------------
-    words = [MAGIC, VERSION, len(code), len(consts), len(tables), n_slots, log_n, log_blowup]
+    # ---- 5. serialise --------------------------------------------------------------------------------------
+    table_memo: dict = {}
+    table_vals = [lw.table_values(e, table_memo) for e in tables]
+    del table_memo
+    if log_n + log_blowup > 32:
+        raise ValueError("tap offsets are stored as 32-bit row indices")
+    words = [MAGIC, VERSION, len(code), len(consts), len(tables), max(n_slots, 1), log_n, log_blowup, len(tap_list), 0, 0, 0, 0, 0, 0, 0]
     off = 0
-    for t in tables:
+    for t in table_vals:
         words += [len(t).bit_length() - 1, off]
         off += len(t)
     if len(tables) & 1:
-        words += [0, 0]                      # keep the instruction area 16-byte aligned
-    for op, d, a, b, imm in code:
-        words += [op | (d << 8), a & 0xFFFFFFFF, b & 0xFFFFFFFF, imm & 0xFFFFFFFF]
+        words += [0, 0]                      # keep the following areas 16-byte aligned
+    for col, toff in tap_list:
+        words += [col, toff]
+    if len(tap_list) & 1:
+        words += [0, 0]
+    for w4 in code:
+        words += [w & 0xFFFFFFFF for w in w4]
     head = struct.pack(f"<{len(words)}I", *words)
     if len(head) % 32:
         head += b"\0" * (32 - len(head) % 32)
-    felts = [l for v in consts for l in _mont_limbs(v)] + [l for t in tables for v in t for l in _mont_limbs(v)]
+    felts = [l for v in consts for l in _mont_limbs(v)] + [l for t in table_vals for v in t for l in _mont_limbs(v)]
     body = np.array(felts, dtype=np.uint64).tobytes() if felts else b""
-    return CompiledProgram(blob=head + body, n_instr=len(code), n_consts=len(consts), n_tables=len(tables), n_slots=n_slots,
-                           n_mul=stats["mul"], n_addsub=stats["addsub"], n_trace_taps=stats["trace"], n_batch_inv=len(batch),
-                           table_sizes=[len(t) for t in tables])
+    return CompiledProgram(blob=head + body, n_instr=len(code), n_consts=len(consts), n_tables=len(tables), n_slots=max(n_slots, 1),
+                           n_mul=stats["mul"], n_addsub=stats["addsub"], n_trace_taps=stats["trace"], n_batch_inv=len(inv_nodes),
+                           table_sizes=[len(t) for t in table_vals], n_red=stats["red"], n_dot=stats["dot"], n_inv=stats["inv"])

@@ -2,38 +2,43 @@
 // straight-line program produced by sandstorm_b200/air/program.py — the flattened Expr DAG of
 // AirConfig::composition_constraint (layouts/src/recursive/air.rs:1184-1200) — on every LDE row.
 //
-// One thread per row i (x_i = 3 * w_N^i).  Row-periodic sub-expressions (zerofiers and their inverses,
-// periodic columns) arrive as lookup tables indexed by i mod T; trace taps read
-// lde[col][(i + offset*blowup) mod N] — neighbouring threads read neighbouring elements of the same
-// column, so every tap is a coalesced 32-byte-per-lane stream served mostly by L2 (each LDE element
-// is touched once per tap offset).  Full-period denominators (X - g^e boundary terms) are inverted
-// together with one batched inversion per row.  Values live in a per-thread slot file.
+// One thread per row i (x_i = 3 * w_N^i).  Operands are fetched where they are used: a slot of the
+// per-thread value file, a constant, an entry of a row-periodic lookup table (zerofiers and their
+// inverses, periodic columns; index i mod T) or a trace tap lde[col][(i + offset) mod N] —
+// neighbouring threads read neighbouring elements of the same column, so every tap is a coalesced
+// 32-byte-per-lane stream served mostly by L1/L2 (each LDE element is touched once per tap offset).
+//
+// The compiler knows an exact upper bound of every value, so the arithmetic here is branch-free: ADD is a
+// raw 256-bit addition, SUBK adds k * p before subtracting, RED is emitted only where a bound would
+// overflow, and a linear combination with general coefficients is one DOT: its products are accumulated
+// unreduced in 512 bits (fp::WideAcc) and Montgomery-reduced once.
 //
 // Algorithmic bytes per row: (C_base + C_ext + 1) * 32 B; field-ops per row are reported by the compiler
 // (CompiledProgram.n_mul / n_addsub).
 #include "ctx.h"
 #include "pedersen.cuh"   // ec::inv_chain
+#include <cstdlib>
 
 using namespace ss;
 
 namespace {
 
-enum Op : uint32_t { OP_NOP, OP_CONST, OP_TRACE, OP_TABLE, OP_X, OP_ADD, OP_SUB, OP_MUL, OP_NEG, OP_INV, OP_BATCHINV, OP_OUT, OP_MULC, OP_ADDC };
-// two instantiations: constraint compositions need ~32 slots and a handful of boundary denominators;
-// DEEP compositions pin one denominator per out-of-domain point (191 + 1 for the starknet layout)
+enum Op : uint32_t { OP_NOP, OP_MOV, OP_ADD, OP_SUBK, OP_RED, OP_MUL, OP_DOT, OP_INV, OP_OUT, OP_COUNT };
+enum Kind : uint32_t { K_SLOT, K_CONST, K_TAP, K_TABLE, K_X, K_COUNT };
+// two instantiations of the slot file: the Cairo compositions and DEEP quotients need < 32 slots
 constexpr int MAX_SLOTS = 256;
-constexpr int MAX_BATCH = 192;
-constexpr int SMALL_SLOTS = 64;
-constexpr int SMALL_BATCH = 32;
+constexpr int SMALL_SLOTS = 32;
 constexpr uint32_t MAGIC = 0x50435353u;
+constexpr uint32_t VERSION = 2;
 constexpr int T_XLO = 20, T_XHI = 21;
 
 struct EvalArgs {
     const uint4 *code;
-    int n_instr;
+    int n_words;
     const Fp *consts;
     const Fp *tables;
     const uint2 *tdesc;        // (log_period, offset)
+    const uint2 *taps;         // (column, row offset mod N)
     const Fp *cols;
     unsigned long long stride;
     int log_N;
@@ -50,58 +55,61 @@ __device__ __forceinline__ Fp ldg_fp(const Fp *p) {
     return v;
 }
 
-template <int SLOTS, int BATCH>
-__global__ void __launch_bounds__(128) constraint_eval_kernel(const EvalArgs A) {
+// operand word: kind << 29 | payload (program.py).  `w` is warp-uniform, so every branch here is uniform.
+__device__ __forceinline__ Fp fetch(const uint32_t w, const Fp *s, const EvalArgs &A, const unsigned long long i) {
+    const uint32_t pay = w & 0x1fffffffu;
+    switch (w >> 29) {
+    case K_SLOT: return s[pay];
+    case K_CONST: return ldg_fp(A.consts + pay);
+    case K_TAP: {
+        const uint2 tp = __ldg(A.taps + pay);
+        const unsigned long long row = (i + tp.y) & ((1ull << A.log_N) - 1);
+        return ldg_fp(A.cols + (unsigned long long)tp.x * A.stride + row);
+    }
+    case K_TABLE: {
+        const uint2 td = __ldg(A.tdesc + pay);
+        return ldg_fp(A.tables + td.y + (i & ((1ull << td.x) - 1)));
+    }
+    default: {                                                                   // K_X
+        Fp v = ldg_fp(A.xlo + (i & 4095ull));
+        if (i >> 12) v = fp::mul(v, ldg_fp(A.xhi + (i >> 12)));
+        return v;
+    }
+    }
+}
+
+// MINB = resident CTAs per SM the register allocation is sized for (5: 96 registers, no spills; 6: 80; 7: 72)
+template <int SLOTS, int MINB>
+__global__ void __launch_bounds__(128, MINB) constraint_eval_kernel(const EvalArgs A) {
     const unsigned long long t = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-    const unsigned long long N = 1ull << A.log_N;
     if (t >= A.row_count) return;
     const unsigned long long i = A.row_begin + t;
     Fp s[SLOTS];
 #pragma unroll 1
-    for (int pc = 0; pc < A.n_instr; ++pc) {
+    for (int pc = 0; pc < A.n_words; ++pc) {
         const uint4 ins = __ldg(A.code + pc);
-        const uint32_t op = ins.x & 0xffu, d = ins.x >> 8, a = ins.y, b = ins.z;
+        const uint32_t op = ins.x & 0xffu, d = (ins.x >> 8) & 0xffu, n = ins.x >> 16;
         switch (op) {
-        case OP_CONST: s[d] = ldg_fp(A.consts + a); break;
-        case OP_TRACE: {
-            const long long off = (long long)(int)ins.w;
-            const unsigned long long row = (unsigned long long)((long long)i + off) & (N - 1);
-            s[d] = ldg_fp(A.cols + (unsigned long long)a * A.stride + row);
-            break;
-        }
-        case OP_TABLE: {
-            const uint2 td = __ldg(A.tdesc + a);
-            s[d] = ldg_fp(A.tables + td.y + (i & ((1ull << td.x) - 1)));
-            break;
-        }
-        case OP_X: {
-            Fp v = ldg_fp(A.xlo + (i & 4095ull));
-            if (i >> 12) v = fp::mul(v, ldg_fp(A.xhi + (i >> 12)));
-            s[d] = v;
-            break;
-        }
-        case OP_ADD: s[d] = fp::add(s[a], s[b]); break;
-        case OP_SUB: s[d] = fp::sub(s[a], s[b]); break;
-        case OP_MUL: s[d] = fp::mul(s[a], s[b]); break;
-        case OP_MULC: s[d] = fp::mul(s[a], ldg_fp(A.consts + b)); break;
-        case OP_ADDC: s[d] = fp::add(s[a], ldg_fp(A.consts + b)); break;
-        case OP_NEG: s[d] = fp::neg(s[a]); break;
-        case OP_INV: s[d] = ec::inv_chain(s[a]); break;
-        case OP_BATCHINV: {
-            // Montgomery's trick over slots [a, a + b)
-            Fp pre[BATCH];
-            Fp acc = fp::one();
-            for (uint32_t k = 0; k < b; ++k) { pre[k] = acc; acc = fp::mul(acc, s[a + k]); }
-            Fp inv = ec::inv_chain(acc);
-            for (uint32_t k = b; k-- > 0;) {
-                const Fp t = fp::mul(inv, pre[k]);
-                inv = fp::mul(inv, s[a + k]);
-                s[a + k] = t;
+        case OP_MOV: s[d] = fetch(ins.y, s, A, i); break;
+        case OP_ADD: s[d] = fp::add_raw(fetch(ins.y, s, A, i), fetch(ins.z, s, A, i)); break;
+        case OP_SUBK: s[d] = fp::sub_kp(fetch(ins.y, s, A, i), fetch(ins.z, s, A, i), n); break;
+        case OP_RED: s[d] = fp::red(s[d]); break;
+        case OP_MUL: s[d] = fp::mul(fetch(ins.y, s, A, i), fetch(ins.z, s, A, i)); break;
+        case OP_DOT: {
+            fp::WideAcc acc;
+            fp::acc_init(acc);
+#pragma unroll 1
+            for (uint32_t k = 0; k < n; k += 2) {
+                const uint4 pr = __ldg(A.code + (++pc));
+                fp::acc_mac(acc, fetch(pr.x, s, A, i), fetch(pr.y, s, A, i));
+                if (k + 1 < n) fp::acc_mac(acc, fetch(pr.z, s, A, i), fetch(pr.w, s, A, i));
             }
+            s[d] = fp::acc_reduce(acc);
             break;
         }
+        case OP_INV: s[d] = ec::inv_chain(fetch(ins.y, s, A, i)); break;
         case OP_OUT: {
-            const Fp v = fp::canon(s[a]);
+            const Fp v = fp::canon(fetch(ins.y, s, A, i));
             uint4 *q = reinterpret_cast<uint4 *>(A.out + i);
             q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
             q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
@@ -137,44 +145,69 @@ ss_status ss_constraint_eval(ss_ctx *ctx, const void *h_program, size_t program_
                              uint64_t col_stride, int n_cols, int log_n, int log_blowup, uint64_t row_begin, uint64_t row_count,
                              void *d_out, void *stream) {
     if (!ctx) return SS_ERR_INVALID;
-    if (!h_program || program_bytes < 32 || !d_lde_cols || !d_out || n_cols < 1)
+    if (!h_program || program_bytes < 64 || !d_lde_cols || !d_out || n_cols < 1)
         return fail(ctx, SS_ERR_INVALID, "ss_constraint_eval: bad arguments");
     const uint32_t *w = static_cast<const uint32_t *>(h_program);
-    if (w[0] != MAGIC || w[1] != 1) return fail(ctx, SS_ERR_INVALID, "ss_constraint_eval: not a program blob (magic/version)");
-    const uint32_t n_instr = w[2], n_consts = w[3], n_tables = w[4], n_slots = w[5];
+    if (w[0] != MAGIC || w[1] != VERSION) return fail(ctx, SS_ERR_INVALID, "ss_constraint_eval: not a program blob (magic/version)");
+    const uint32_t n_words = w[2], n_consts = w[3], n_tables = w[4], n_slots = w[5], n_taps = w[8];
     if ((int)w[6] != log_n || (int)w[7] != log_blowup)
         return fail(ctx, SS_ERR_INVALID, "ss_constraint_eval: program compiled for log_n=%u blowup=%u, called with %d/%d", w[6], w[7], log_n, log_blowup);
     if (n_slots > (uint32_t)MAX_SLOTS) return fail(ctx, SS_ERR_UNSUPPORTED, "ss_constraint_eval: %u slots > %d", n_slots, MAX_SLOTS);
     const int log_N = log_n + log_blowup;
+    if (log_N > 32) return fail(ctx, SS_ERR_INVALID, "ss_constraint_eval: domain too large");
     if (col_stride < (1ull << log_N)) return fail(ctx, SS_ERR_INVALID, "ss_constraint_eval: col_stride too small");
     const size_t n_tdesc = (size_t)n_tables + (n_tables & 1u);          // descriptor area padded to 16 bytes
-    size_t head_words = 8 + 2 * n_tdesc + 4 * (size_t)n_instr;
+    const size_t n_tapd = (size_t)n_taps + (n_taps & 1u);
+    size_t head_words = 16 + 2 * n_tdesc + 2 * n_tapd + 4 * (size_t)n_words;
     size_t head_bytes = (head_words * 4 + 31) / 32 * 32;
+    if (head_bytes > program_bytes) return fail(ctx, SS_ERR_INVALID, "ss_constraint_eval: blob size mismatch");
     size_t table_elems = 0;
     for (uint32_t t = 0; t < n_tables; ++t) {
-        const uint32_t lp = w[8 + 2 * t], off = w[8 + 2 * t + 1];
+        const uint32_t lp = w[16 + 2 * t], off = w[16 + 2 * t + 1];
         if (lp > 20 || off != table_elems) return fail(ctx, SS_ERR_INVALID, "ss_constraint_eval: corrupt table descriptor %u", t);
         table_elems += (size_t)1 << lp;
     }
     if (program_bytes != head_bytes + 32 * ((size_t)n_consts + table_elems))
         return fail(ctx, SS_ERR_INVALID, "ss_constraint_eval: blob size mismatch");
-    // validate operands so that a bad program cannot index outside the slot file / matrix
-    const uint32_t *code = w + 8 + 2 * n_tdesc;
-    for (uint32_t pc = 0; pc < n_instr; ++pc) {
-        const uint32_t op = code[4 * pc] & 0xff, d = code[4 * pc] >> 8, a = code[4 * pc + 1], b = code[4 * pc + 2];
-        bool ok = d < n_slots || op == OP_OUT || op == OP_BATCHINV || op == OP_NOP;
+    // validate every operand so that a bad program cannot index outside the slot file, the tables or the matrix
+    const uint32_t *tapd = w + 16 + 2 * n_tdesc;
+    for (uint32_t t = 0; t < n_taps; ++t)
+        if (tapd[2 * t] >= (uint32_t)n_cols || (uint64_t)tapd[2 * t + 1] >= (1ull << log_N))
+            return fail(ctx, SS_ERR_INVALID, "ss_constraint_eval: tap %u outside the matrix", t);
+    const uint32_t *code = tapd + 2 * n_tapd;
+    auto operand_ok = [&](uint32_t word) {
+        const uint32_t pay = word & 0x1fffffffu;
+        switch (word >> 29) {
+        case K_SLOT: return pay < n_slots;
+        case K_CONST: return pay < n_consts;
+        case K_TAP: return pay < n_taps;
+        case K_TABLE: return pay < n_tables;
+        case K_X: return true;
+        default: return false;
+        }
+    };
+    for (uint32_t pc = 0; pc < n_words; ++pc) {
+        const uint32_t w0 = code[4 * pc], op = w0 & 0xff, d = (w0 >> 8) & 0xff, n = w0 >> 16;
+        bool ok = d < n_slots || op == OP_OUT || op == OP_NOP;
         switch (op) {
-        case OP_CONST: ok = ok && a < n_consts; break;
-        case OP_TRACE: ok = ok && a < (uint32_t)n_cols; break;
-        case OP_TABLE: ok = ok && a < n_tables; break;
-        case OP_ADD: case OP_SUB: case OP_MUL: ok = ok && a < n_slots && b < n_slots; break;
-        case OP_MULC: case OP_ADDC: ok = ok && a < n_slots && b < n_consts; break;
-        case OP_NEG: case OP_INV: case OP_OUT: ok = ok && a < n_slots; break;
-        case OP_BATCHINV: ok = a + b <= n_slots && b <= (uint32_t)MAX_BATCH; break;
-        case OP_X: case OP_NOP: break;
+        case OP_NOP: break;
+        case OP_MOV: case OP_INV: case OP_OUT: ok = ok && operand_ok(code[4 * pc + 1]); break;
+        case OP_ADD: case OP_MUL: ok = ok && operand_ok(code[4 * pc + 1]) && operand_ok(code[4 * pc + 2]); break;
+        case OP_SUBK: ok = ok && n <= 31 && operand_ok(code[4 * pc + 1]) && operand_ok(code[4 * pc + 2]); break;
+        case OP_RED: break;
+        case OP_DOT: {
+            const uint32_t extra = (n + 1) / 2;
+            ok = ok && n >= 1 && pc + extra < n_words;
+            for (uint32_t k = 0; ok && k < n; ++k) {
+                const uint32_t *pr = code + 4 * (pc + 1 + k / 2) + 2 * (k & 1);
+                ok = operand_ok(pr[0]) && operand_ok(pr[1]);
+            }
+            if (ok) pc += extra;
+            break;
+        }
         default: ok = false;
         }
-        if (!ok) return fail(ctx, SS_ERR_INVALID, "ss_constraint_eval: invalid instruction %u (op %u)", pc, op);
+        if (!ok) return fail(ctx, SS_ERR_INVALID, "ss_constraint_eval: invalid instruction at word %u (op %u)", pc, op);
     }
     SS_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = pick_stream(ctx, stream);
@@ -188,9 +221,10 @@ ss_status ss_constraint_eval(ss_ctx *ctx, const void *h_program, size_t program_
     if ((rc = cached_table(ctx, {T_XLO, log_N, 0}, N < 4096 ? N : 4096, fill_xlo, &xlo))) return rc;
     if ((rc = cached_table(ctx, {T_XHI, log_N, 0}, N <= 4096 ? 1 : N / 4096, fill_xhi, &xhi))) return rc;
     EvalArgs A;
-    A.tdesc = reinterpret_cast<const uint2 *>(d_prog + 32);
-    A.code = reinterpret_cast<const uint4 *>(d_prog + 32 + 8 * n_tdesc);
-    A.n_instr = (int)n_instr;
+    A.tdesc = reinterpret_cast<const uint2 *>(d_prog + 64);
+    A.taps = reinterpret_cast<const uint2 *>(d_prog + 64 + 8 * n_tdesc);
+    A.code = reinterpret_cast<const uint4 *>(d_prog + 64 + 8 * n_tdesc + 8 * n_tapd);
+    A.n_words = (int)n_words;
     A.consts = reinterpret_cast<const Fp *>(d_prog + head_bytes);
     A.tables = A.consts + n_consts;
     A.cols = static_cast<const Fp *>(d_lde_cols);
@@ -201,13 +235,16 @@ ss_status ss_constraint_eval(ss_ctx *ctx, const void *h_program, size_t program_
     if (row_count == 0) { row_begin = 0; row_count = N; }                 // 0 = the whole domain
     if (row_begin + row_count > N) return fail(ctx, SS_ERR_INVALID, "ss_constraint_eval: row range outside the domain");
     A.row_begin = row_begin; A.row_count = row_count;
-    uint32_t max_batch = 0;
-    for (uint32_t pc = 0; pc < n_instr; ++pc)
-        if ((code[4 * pc] & 0xff) == OP_BATCHINV && code[4 * pc + 2] > max_batch) max_batch = code[4 * pc + 2];
-    if (n_slots <= (uint32_t)SMALL_SLOTS && max_batch <= (uint32_t)SMALL_BATCH)
-        constraint_eval_kernel<SMALL_SLOTS, SMALL_BATCH><<<(unsigned)((row_count + 127) / 128), 128, 0, st>>>(A);
+    static const int minb = [] { const char *e = getenv("SS_CE_MINB"); return e ? atoi(e) : 5; }();   // tuning switch
+    const unsigned grid = (unsigned)((row_count + 127) / 128);
+    if (n_slots > (uint32_t)SMALL_SLOTS)
+        constraint_eval_kernel<MAX_SLOTS, 5><<<grid, 128, 0, st>>>(A);
+    else if (minb >= 7)
+        constraint_eval_kernel<SMALL_SLOTS, 7><<<grid, 128, 0, st>>>(A);
+    else if (minb == 6)
+        constraint_eval_kernel<SMALL_SLOTS, 6><<<grid, 128, 0, st>>>(A);
     else
-        constraint_eval_kernel<MAX_SLOTS, MAX_BATCH><<<(unsigned)((row_count + 127) / 128), 128, 0, st>>>(A);
+        constraint_eval_kernel<SMALL_SLOTS, 5><<<grid, 128, 0, st>>>(A);
     ctx->launches++;
     SS_CUDA_CHECK(ctx, cudaGetLastError());
     SS_CUDA_CHECK(ctx, cudaFreeAsync(d_prog, st));

@@ -246,6 +246,98 @@ SS_HD Fp canon(const Fp &x) {
     return r;
 }
 
+// ---- primitives of the constraint-program interpreter (constraint_eval.cu) ------------------------
+// The compiler (sandstorm_b200/air/program.py) tracks an exact upper bound of every value, so the
+// device never tests magnitudes: it adds raw, subtracts with a pre-computed multiple of p and
+// reduces only where the compiler asks.
+
+// any x < 2^256  ->  congruent value < 2^252:  x -= max((x >> 251) - 1, 0) * p
+SS_HD Fp red(const Fp &x) {
+    using namespace ptx;
+    const uint32_t q = x.l[7] >> 27;
+    const uint32_t m = q - (q != 0u ? 1u : 0u);
+    Fp r;
+    r.l[0] = sub_cc(x.l[0], m);
+#pragma unroll
+    for (int i = 1; i < 6; ++i) r.l[i] = subc_cc(x.l[i], 0u);
+    r.l[6] = subc_cc(x.l[6], 17u * m);
+    r.l[7] = subc(x.l[7], m << 27);
+    return r;
+}
+// a - b + k*p for a run-time k in [0, 31]; exact when k*p >= b and a + k*p < 2^256
+SS_HD Fp sub_kp(const Fp &a, const Fp &b, uint32_t k) {
+    using namespace ptx;
+    Fp r;
+    r.l[0] = sub_cc(a.l[0], b.l[0]);
+#pragma unroll
+    for (int i = 1; i < 7; ++i) r.l[i] = subc_cc(a.l[i], b.l[i]);
+    r.l[7] = subc(a.l[7], b.l[7]);
+    r.l[0] = add_cc(r.l[0], k);
+#pragma unroll
+    for (int i = 1; i < 6; ++i) r.l[i] = addc_cc(r.l[i], 0u);
+    r.l[6] = addc_cc(r.l[6], 17u * k);
+    r.l[7] = addc(r.l[7], k << 27);
+    return r;
+}
+
+// Unreduced sum of products  sum_k a_k * b_k + p * 2^256  (< 2^512, guaranteed by the compiler), kept as
+// the two interleaved accumulators of mul_wide_plus_p plus carry counters: the carry out of every
+// 4-product chain is counted at its limb position instead of being rippled to the top.
+struct WideAcc {
+    uint32_t E[16], O[16];   // O[k] sits at limb position k + 1
+    uint32_t CE[4], CO[4];   // carries into E positions 8,10,12,14 and O indices 8,10,12,14
+};
+SS_HD void acc_init(WideAcc &w) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { w.E[i] = 0; w.O[i] = 0; }
+    w.E[8] = SS_P0; w.E[14] = SS_P6; w.E[15] = SS_P7;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { w.CE[i] = 0; w.CO[i] = 0; }
+}
+SS_HD void acc_mac(WideAcc &w, const Fp &a, const Fp &b) {
+    using namespace ptx;
+    uint32_t (&E)[16] = w.E;
+    uint32_t (&O)[16] = w.O;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t bi = b.l[i];
+        if ((i & 1) == 0) {
+            mad4_chain(E[i], E[i + 1], E[i + 2], E[i + 3], E[i + 4], E[i + 5], E[i + 6], E[i + 7], w.CE[i / 2],
+                       a.l[0], a.l[2], a.l[4], a.l[6], bi);
+            mad4_chain(O[i], O[i + 1], O[i + 2], O[i + 3], O[i + 4], O[i + 5], O[i + 6], O[i + 7], w.CO[i / 2],
+                       a.l[1], a.l[3], a.l[5], a.l[7], bi);
+        } else {
+            if (i < 7)
+                mad4_chain(E[i + 1], E[i + 2], E[i + 3], E[i + 4], E[i + 5], E[i + 6], E[i + 7], E[i + 8], w.CE[(i + 1) / 2],
+                           a.l[1], a.l[3], a.l[5], a.l[7], bi);
+            else
+                mad4_chain_top(E[8], E[9], E[10], E[11], E[12], E[13], E[14], E[15], a.l[1], a.l[3], a.l[5], a.l[7], bi);
+            mad4_chain(O[i - 1], O[i], O[i + 1], O[i + 2], O[i + 3], O[i + 4], O[i + 5], O[i + 6], w.CO[(i - 1) / 2],
+                       a.l[0], a.l[2], a.l[4], a.l[6], bi);
+        }
+    }
+}
+// (acc - q*p) / 2^256 : in (S/R, S/R + p] for S = sum of the products
+SS_HD Fp acc_reduce(const WideAcc &w) {
+    using namespace ptx;
+    uint32_t T[16];
+    T[0] = w.E[0];
+    T[1] = add_cc(w.E[1], w.O[0]);
+#pragma unroll
+    for (int k = 2; k < 15; ++k) T[k] = addc_cc(w.E[k], w.O[k - 1]);
+    T[15] = addc(w.E[15], w.O[14]);
+    // carry counters: CE[j] at limb 8 + 2j, CO[j] at limb 9 + 2j
+    T[8] = add_cc(T[8], w.CE[0]);
+    T[9] = addc_cc(T[9], w.CO[0]);
+    T[10] = addc_cc(T[10], w.CE[1]);
+    T[11] = addc_cc(T[11], w.CO[1]);
+    T[12] = addc_cc(T[12], w.CE[2]);
+    T[13] = addc_cc(T[13], w.CO[2]);
+    T[14] = addc_cc(T[14], w.CE[3]);
+    T[15] = addc(T[15], w.CO[3]);
+    return mont_reduce(T);
+}
+
 SS_HD bool is_zero_canon(const Fp &a) {
     uint32_t o = 0;
 #pragma unroll

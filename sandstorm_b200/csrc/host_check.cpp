@@ -44,6 +44,24 @@ void hc_fp_inv(const uint32_t *a, uint32_t *out) {
     Fp x; std::memcpy(x.l, a, 32);
     Fp r = fp::canon(fp::inv(x)); std::memcpy(out, r.l, 32);
 }
+void hc_fp_red(const uint32_t *a, uint32_t *out) {
+    Fp x; std::memcpy(x.l, a, 32);
+    Fp r = fp::red(x); std::memcpy(out, r.l, 32);
+}
+void hc_fp_sub_kp(const uint32_t *a, const uint32_t *b, uint32_t k, uint32_t *out) {
+    Fp x, y; std::memcpy(x.l, a, 32); std::memcpy(y.l, b, 32);
+    Fp r = fp::sub_kp(x, y, k); std::memcpy(out, r.l, 32);
+}
+// out = Montgomery reduction of sum_k a[k] * b[k] (n terms of 8 limbs each)
+void hc_fp_dot(const uint32_t *a, const uint32_t *b, int n, uint32_t *out) {
+    fp::WideAcc w;
+    fp::acc_init(w);
+    for (int k = 0; k < n; ++k) {
+        Fp x, y; std::memcpy(x.l, a + 8 * k, 32); std::memcpy(y.l, b + 8 * k, 32);
+        fp::acc_mac(w, x, y);
+    }
+    Fp r = fp::acc_reduce(w); std::memcpy(out, r.l, 32);
+}
 void hc_fp_from_u32(uint32_t v, uint32_t *out) {
     Fp r = fp::from_u32(v); std::memcpy(out, r.l, 32);
 }

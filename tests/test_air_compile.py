@@ -1,8 +1,6 @@
 """CPU-only: the Expr -> program compiler (period analysis, table extraction, slot allocation).
 The program is executed by a tiny Python interpreter of the blob and compared with the independent
 tree evaluator — this pins the blob format the CUDA kernel consumes."""
-import struct
-
 import numpy as np
 import pytest
 
@@ -10,46 +8,7 @@ from air_ref import eval_expr
 from sandstorm_b200.air import Challenge, Constant, Hint, Periodic, Trace, X, compile_program, composition_constraint
 from sandstorm_b200.air.expr import P
 
-R = 2**256
-RINV = pow(R, -1, P)
-
-
-def run_blob(blob, i, lde_int, log_N):
-    w = struct.unpack_from("<8I", blob, 0)
-    assert w[0] == 0x50435353
-    n_instr, n_consts, n_tables, n_slots = w[2], w[3], w[4], w[5]
-    nt = n_tables + (n_tables & 1)
-    tdesc = struct.unpack_from(f"<{2 * n_tables}I", blob, 32)
-    code = struct.unpack_from(f"<{4 * n_instr}I", blob, 32 + 8 * nt)
-    head = (32 + 8 * nt + 16 * n_instr + 31) // 32 * 32
-    felts = np.frombuffer(blob, dtype=np.uint64, offset=head).reshape(-1, 4)
-    val = lambda k: (int(felts[k][0]) | int(felts[k][1]) << 64 | int(felts[k][2]) << 128 | int(felts[k][3]) << 192) * RINV % P
-    N = 1 << log_N
-    wN = pow(3, (P - 1) // N, P)
-    s = [None] * n_slots
-    out = None
-    for pc in range(n_instr):
-        op, d = code[4 * pc] & 0xFF, code[4 * pc] >> 8
-        a, b, imm = code[4 * pc + 1], code[4 * pc + 2], code[4 * pc + 3]
-        if imm >= 1 << 31:
-            imm -= 1 << 32
-        if op == 1: s[d] = val(a)
-        elif op == 2: s[d] = lde_int[a][(i + imm) % N]
-        elif op == 3: s[d] = val(n_consts + tdesc[2 * a + 1] + (i & ((1 << tdesc[2 * a]) - 1)))
-        elif op == 4: s[d] = 3 * pow(wN, i, P) % P
-        elif op == 5: s[d] = (s[a] + s[b]) % P
-        elif op == 6: s[d] = (s[a] - s[b]) % P
-        elif op == 7: s[d] = s[a] * s[b] % P
-        elif op == 8: s[d] = -s[a] % P
-        elif op == 9: s[d] = pow(s[a], -1, P)
-        elif op == 10:
-            for k in range(a, a + b):
-                s[k] = pow(s[k], -1, P)
-        elif op == 11: out = s[a]
-        elif op == 12: s[d] = s[a] * val(b) % P
-        elif op == 13: s[d] = (s[a] + val(b)) % P
-        else: raise AssertionError(op)
-    return out
+from blob_emu import run_blob
 
 
 def toy_air(n):
