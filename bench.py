@@ -283,7 +283,13 @@ class HotPath:
 class FullHotPath(HotPath):
     """Every device stage of the prove loop (sandstorm_b200/prover.py) with the real starknet AIR, on 1..8 ranks."""
 
-    NTT_STAGES = ("lde_base", "lde_ext", "ntt_comp_inv", "ntt_comp_fwd")
+    NTT_STAGES = ("lde_base", "lde_ext", "ntt_comp_inv", "ntt_comp_fwd", "deep_lde")
+
+    def ntt_field_ops(self):
+        return HotPath.ntt_field_ops(self) + ntt_ops(self.log_n) + ntt_ops(self.log_N)      # + extension of the DEEP quotient
+
+    def ntt_algo_bytes(self):
+        return HotPath.ntt_algo_bytes(self) + ntt_algo_bytes(1, self.log_n) + ntt_algo_bytes(1, self.log_N)
 
     def __init__(self, log_n: int, rank: int = 0, world: int = 1, seed: int = 0xB200):
         import torch
@@ -416,7 +422,7 @@ def gpu_arm(args):
     for a, b in per_step:
         for k, v in stage_times(hp.events[a:b]).items():
             stages[k] = stages.get(k, 0.0) + v / args.steps
-    ntt_ms = sum(stages.get(k, 0.0) for k in HotPath.NTT_STAGES)
+    ntt_ms = sum(stages.get(k, 0.0) for k in type(hp).NTT_STAGES)
     t = torch.tensor([total_ms / args.steps, ntt_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)

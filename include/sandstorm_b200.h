@@ -67,6 +67,12 @@ const char *ss_last_error(const ss_ctx *ctx);
 ss_status ss_sync(ss_ctx *ctx);
 /* number of CUDA kernels this ctx has launched so far (bench.py reports the per-step delta) */
 uint64_t ss_kernel_launches(const ss_ctx *ctx);
+/* tuning switches and read-back values of a context (no reference counterpart).  Keys:
+ *   "ce_aot"      1 (default) = ss_constraint_eval may use a kernel specialised at build time, 0 = always interpret
+ *   "ce_minb"     resident CTAs per SM the interpreter is compiled for (5, 6 or 7)
+ *   "ce_last_aot" (read) 1 when the last ss_constraint_eval call ran a specialised kernel */
+ss_status ss_set_option(ss_ctx *ctx, const char *key, int64_t value);
+int64_t ss_get_option(const ss_ctx *ctx, const char *key, int64_t dflt);
 /* thin wrappers so that a host without the CUDA runtime (Rust) can own device buffers;
  * replaces ministark_gpu's GpuAllocator / GpuVec role (layouts/src/recursive/trace.rs:55-56,115) */
 ss_status ss_malloc(ss_ctx *ctx, size_t bytes, void **d_ptr);
@@ -150,11 +156,14 @@ ss_status ss_poly_eval(ss_ctx *ctx, ss_field field, const void *d_coeffs, uint64
 /* ------------------------------------------------------------------ constraint evaluation (§8 a4-a7)
  * Evaluates a compiled composition-constraint program (the Expr DAG of
  * AirConfig::composition_constraint, layouts/src/recursive/air.rs:1184-1200, flattened by the host
- * into straight-line code; format in sandstorm_b200/air/program.py) on every LDE row.          */
+ * into straight-line code; format in sandstorm_b200/air/program.py) on every LDE row — or on every
+ * 2^log_row_step-th row: a quotient of degree < n such as the DEEP composition is fixed by its n values on
+ * the sub-coset of the rows that are multiples of the blowup, and is extended with ss_ntt afterwards.   */
 ss_status ss_constraint_eval(ss_ctx *ctx, const void *h_program, size_t program_bytes,
                              const void *d_lde_cols, uint64_t col_stride, int n_cols, int log_n,
                              int log_blowup, uint64_t row_begin, uint64_t row_count /* 0 = all rows */,
-                             void *d_out /* indexed by absolute row */, void *stream);
+                             int log_row_step /* rows row_begin + k * 2^log_row_step, k < row_count */,
+                             void *d_out /* indexed by (absolute row >> log_row_step) */, void *stream);
 
 #ifdef __cplusplus
 }

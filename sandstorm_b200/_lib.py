@@ -25,6 +25,8 @@ SIGNATURES = {
     "ss_last_error": (c_char_p, [c_void_p]),
     "ss_sync": (c_int, [c_void_p]),
     "ss_kernel_launches": (c_uint64, [c_void_p]),
+    "ss_set_option": (c_int, [c_void_p, c_char_p, ctypes.c_int64]),
+    "ss_get_option": (ctypes.c_int64, [c_void_p, c_char_p, ctypes.c_int64]),
     "ss_malloc": (c_int, [c_void_p, c_size_t, POINTER(c_void_p)]),
     "ss_free": (c_int, [c_void_p, c_void_p]),
     "ss_host_register": (c_int, [c_void_p, c_void_p, c_size_t]),
@@ -46,7 +48,7 @@ SIGNATURES = {
     "ss_fri_fold": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_uint64, c_uint64, c_void_p, c_void_p]),
     "ss_inv_x_minus_c": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "ss_poly_eval": (c_int, [c_void_p, c_int, c_void_p, c_uint64, c_int, c_int, POINTER(ctypes.c_int32), c_void_p, c_size_t, c_void_p]),
-    "ss_constraint_eval": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_uint64, c_int, c_int, c_int, c_uint64, c_uint64, c_void_p, c_void_p]),
+    "ss_constraint_eval": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_uint64, c_int, c_int, c_int, c_uint64, c_uint64, c_int, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -302,7 +302,7 @@ LEAF_KINDS = ("const", "table", "trace")
 
 
 def compile_program(expr: Expr, log_n: int, log_blowup: int, challenges=(), hints=(), composition_coeffs=(0,),
-                    max_slots: int = 256, regroup: bool = True) -> CompiledProgram:
+                    max_slots: int = 256, regroup: bool = True, with_tables: bool = True) -> CompiledProgram:
     """expr: the composition constraint (or any Expr).  challenges / hints / composition_coeffs: canonical ints."""
     import sys
     sys.setrecursionlimit(max(sys.getrecursionlimit(), 200000))
@@ -756,7 +756,8 @@ def compile_program(expr: Expr, log_n: int, log_blowup: int, challenges=(), hint
 
     # ---- 5. serialise --------------------------------------------------------------------------------------
     table_memo: dict = {}
-    table_vals = [lw.table_values(e, table_memo) for e in tables]
+    # with_tables=False (build-time code generation): only the shape of the tables is needed
+    table_vals = [lw.table_values(e, table_memo) if with_tables else [0] * lw.period(e) for e in tables]
     del table_memo
     if log_n + log_blowup > 32:
         raise ValueError("tap offsets are stored as 32-bit row indices")
@@ -781,3 +782,21 @@ def compile_program(expr: Expr, log_n: int, log_blowup: int, challenges=(), hint
     return CompiledProgram(blob=head + body, n_instr=len(code), n_consts=len(consts), n_tables=len(tables), n_slots=max(n_slots, 1),
                            n_mul=stats["mul"], n_addsub=stats["addsub"], n_trace_taps=stats["trace"], n_batch_inv=len(inv_nodes),
                            table_sizes=[len(t) for t in table_vals], n_red=stats["red"], n_dot=stats["dot"], n_inv=stats["inv"])
+
+
+def structure_hash(blob: bytes) -> int:
+    """64-bit FNV-1a over the structural part of a program blob: counts, blowup, table periods, tap columns and
+    the code words — everything except the trace length, the tap row offsets and the constant / table VALUES.
+    ss_constraint_eval computes the same hash to pick a kernel specialised at build time (tools/gen_ce_kernels.py)."""
+    w = struct.unpack_from("<16I", blob, 0)
+    n_words, n_consts, n_tables, n_slots, n_taps = w[2], w[3], w[4], w[5], w[8]
+    nt, ntap = n_tables + (n_tables & 1), n_taps + (n_taps & 1)
+    tdesc = struct.unpack_from(f"<{2 * n_tables}I", blob, 64)
+    taps = struct.unpack_from(f"<{2 * n_taps}I", blob, 64 + 8 * nt)
+    code = struct.unpack_from(f"<{4 * n_words}I", blob, 64 + 8 * nt + 8 * ntap)
+    stream = [n_words, n_consts, n_tables, n_slots, w[7], n_taps] + [tdesc[2 * t] for t in range(n_tables)] + [taps[2 * t] for t in range(n_taps)] + list(code)
+    h = 0xCBF29CE484222325
+    for v in stream:
+        for sh in (0, 8, 16, 24):
+            h = ((h ^ ((v >> sh) & 0xFF)) * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
+    return h

@@ -83,6 +83,13 @@ ss_status ss_sync(ss_ctx *ctx) {
 
 uint64_t ss_kernel_launches(const ss_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+ss_status ss_set_option(ss_ctx *ctx, const char *key, int64_t value) {
+    if (!ctx || !key) return SS_ERR_INVALID;
+    ctx->options[key] = value;
+    return SS_OK;
+}
+int64_t ss_get_option(const ss_ctx *ctx, const char *key, int64_t dflt) { return (ctx && key) ? option(ctx, key, dflt) : dflt; }
+
 ss_status ss_malloc(ss_ctx *ctx, size_t bytes, void **d_ptr) {
     if (!ctx || !d_ptr) return SS_ERR_INVALID;
     SS_CUDA_CHECK(ctx, cudaMalloc(d_ptr, bytes));

@@ -44,7 +44,8 @@ struct EvalArgs {
     int log_N;
     const Fp *xlo, *xhi;       // 3 * w_N^i (i < 4096), w_N^(4096 i)
     Fp *out;
-    unsigned long long row_begin, row_count;   // rows [row_begin, row_begin + row_count) of the LDE domain
+    unsigned long long row_begin, row_count;   // rows row_begin + (k << log_step), k < row_count, of the LDE domain
+    int log_step;
 };
 
 __device__ __forceinline__ Fp ldg_fp(const Fp *p) {
@@ -83,7 +84,7 @@ template <int SLOTS, int MINB>
 __global__ void __launch_bounds__(128, MINB) constraint_eval_kernel(const EvalArgs A) {
     const unsigned long long t = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     if (t >= A.row_count) return;
-    const unsigned long long i = A.row_begin + t;
+    const unsigned long long i = A.row_begin + (t << A.log_step);
     Fp s[SLOTS];
 #pragma unroll 1
     for (int pc = 0; pc < A.n_words; ++pc) {
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(128, MINB) constraint_eval_kernel(const EvalAr
         case OP_INV: s[d] = ec::inv_chain(fetch(ins.y, s, A, i)); break;
         case OP_OUT: {
             const Fp v = fp::canon(fetch(ins.y, s, A, i));
-            uint4 *q = reinterpret_cast<uint4 *>(A.out + i);
+            uint4 *q = reinterpret_cast<uint4 *>(A.out + (i >> A.log_step));
             q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
             q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
             break;
@@ -118,6 +119,56 @@ __global__ void __launch_bounds__(128, MINB) constraint_eval_kernel(const EvalAr
         default: break;
         }
     }
+}
+
+// ---- build-time specialisations (tools/gen_ce_kernels.py): the same programs as straight-line code --------
+// Run-time values the generated code indexes with literals; passed as a __grid_constant__ kernel parameter,
+// i.e. they live in the constant bank and cost no load instruction.
+struct GenArgs {
+    uint32_t tap_off[1024];    // row offset of tap k (mod N)
+    uint32_t tab_off[128];     // element offset of table t inside the table area
+};
+struct Wide { uint32_t t[16]; };
+
+// One shared copy of the 8x8-limb product / reduction: the straight-line callers stay short (instruction
+// cache), and ptxas keeps arguments and results in registers (no stack traffic — checked in the SASS).
+__device__ __noinline__ Fp mul_ni(Fp a, Fp b) { return fp::mul(a, b); }
+__device__ __noinline__ Wide wide_p_ni(Fp a, Fp b) { Wide w; fp::mul_wide_plus_p<true>(w.t, a, b); return w; }
+__device__ __noinline__ Wide wide_ni(Fp a, Fp b) { Wide w; fp::mul_wide_plus_p<false>(w.t, a, b); return w; }
+__device__ __noinline__ Fp reduce_ni(Wide w) { return fp::mont_reduce(w.t); }
+__device__ __forceinline__ void wide_add(Wide &acc, const Wide &w) {
+    using namespace ptx;
+    acc.t[0] = add_cc(acc.t[0], w.t[0]);
+#pragma unroll
+    for (int k = 1; k < 15; ++k) acc.t[k] = addc_cc(acc.t[k], w.t[k]);
+    acc.t[15] = addc(acc.t[15], w.t[15]);
+}
+__device__ __forceinline__ Fp fetch_x(const EvalArgs &A, const unsigned long long i) {
+    Fp v = ldg_fp(A.xlo + (i & 4095ull));
+    if (i >> 12) v = mul_ni(v, ldg_fp(A.xhi + (i >> 12)));
+    return v;
+}
+__device__ __forceinline__ void store_out(Fp *dst, const Fp &v) {
+    uint4 *q = reinterpret_cast<uint4 *>(dst);
+    q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+
+#include "ce_gen.cuh"
+
+// 64-bit FNV-1a over the structural part of the blob — the mirror of program.py structure_hash()
+unsigned long long structure_hash(const uint32_t *w, size_t n_tdesc, size_t n_tapd) {
+    const uint32_t n_words = w[2], n_tables = w[4], n_taps = w[8];
+    unsigned long long h = 0xCBF29CE484222325ull;
+    auto mix = [&](uint32_t v) {
+        for (int sh = 0; sh < 32; sh += 8) h = (h ^ ((v >> sh) & 0xffu)) * 0x100000001B3ull;
+    };
+    mix(n_words); mix(w[3]); mix(n_tables); mix(w[5]); mix(w[7]); mix(n_taps);
+    const uint32_t *tdesc = w + 16, *tapd = tdesc + 2 * n_tdesc, *code = tapd + 2 * n_tapd;
+    for (uint32_t t = 0; t < n_tables; ++t) mix(tdesc[2 * t]);
+    for (uint32_t t = 0; t < n_taps; ++t) mix(tapd[2 * t]);
+    for (size_t k = 0; k < 4 * (size_t)n_words; ++k) mix(code[k]);
+    return h;
 }
 
 Fp host_root(int log_n) {
@@ -143,7 +194,7 @@ extern "C" {
 
 ss_status ss_constraint_eval(ss_ctx *ctx, const void *h_program, size_t program_bytes, const void *d_lde_cols,
                              uint64_t col_stride, int n_cols, int log_n, int log_blowup, uint64_t row_begin, uint64_t row_count,
-                             void *d_out, void *stream) {
+                             int log_row_step, void *d_out, void *stream) {
     if (!ctx) return SS_ERR_INVALID;
     if (!h_program || program_bytes < 64 || !d_lde_cols || !d_out || n_cols < 1)
         return fail(ctx, SS_ERR_INVALID, "ss_constraint_eval: bad arguments");
@@ -232,12 +283,31 @@ ss_status ss_constraint_eval(ss_ctx *ctx, const void *h_program, size_t program_
     A.log_N = log_N;
     A.xlo = xlo; A.xhi = xhi;
     A.out = static_cast<Fp *>(d_out);
-    if (row_count == 0) { row_begin = 0; row_count = N; }                 // 0 = the whole domain
-    if (row_begin + row_count > N) return fail(ctx, SS_ERR_INVALID, "ss_constraint_eval: row range outside the domain");
-    A.row_begin = row_begin; A.row_count = row_count;
-    static const int minb = [] { const char *e = getenv("SS_CE_MINB"); return e ? atoi(e) : 5; }();   // tuning switch
+    if (log_row_step < 0 || log_row_step > log_N) return fail(ctx, SS_ERR_INVALID, "ss_constraint_eval: bad row step");
+    if (row_count == 0) { row_begin = 0; row_count = N >> log_row_step; }   // 0 = the whole domain
+    if ((row_begin & ((1ull << log_row_step) - 1)) || row_begin + (row_count << log_row_step) > N)
+        return fail(ctx, SS_ERR_INVALID, "ss_constraint_eval: row range outside the domain");
+    A.row_begin = row_begin; A.row_count = row_count; A.log_step = log_row_step;
+    // tuning switches: ss_set_option, with the environment as the default
+    static const int env_minb = [] { const char *e = getenv("SS_CE_MINB"); return e ? atoi(e) : 5; }();
+    static const int env_aot = [] { const char *e = getenv("SS_CE_AOT"); return e ? atoi(e) : 1; }();
+    const int minb = (int)option(ctx, "ce_minb", env_minb);
+    const bool use_gen = option(ctx, "ce_aot", env_aot) != 0;
     const unsigned grid = (unsigned)((row_count + 127) / 128);
-    if (n_slots > (uint32_t)SMALL_SLOTS)
+    const GenEntry *gen = nullptr;
+    if (use_gen && n_taps <= 1024 && n_tables <= 128) {
+        const unsigned long long h = structure_hash(w, n_tdesc, n_tapd);
+        const int want = (int)option(ctx, "ce_aot_minb", 0);            // 0 = the variant chosen at build time
+        for (const GenEntry &e : GEN_KERNELS)
+            if (e.hash == h && (want ? e.minb == want : e.dflt)) gen = &e;
+    }
+    ctx->options["ce_last_aot"] = gen ? 1 : 0;
+    if (gen) {
+        GenArgs G;
+        for (uint32_t t = 0; t < n_taps; ++t) G.tap_off[t] = tapd[2 * t + 1];
+        for (uint32_t t = 0; t < n_tables; ++t) G.tab_off[t] = w[16 + 2 * t + 1];
+        gen->kernel<<<grid, 128, 0, st>>>(A, G);
+    } else if (n_slots > (uint32_t)SMALL_SLOTS)
         constraint_eval_kernel<MAX_SLOTS, 5><<<grid, 128, 0, st>>>(A);
     else if (minb >= 7)
         constraint_eval_kernel<SMALL_SLOTS, 7><<<grid, 128, 0, st>>>(A);

@@ -21,9 +21,15 @@ struct ss_ctx {
     size_t scratch_bytes = 0;
     int sm_count = 148;
     unsigned long long launches = 0;          // kernels launched by this ctx (ss_kernel_launches)
+    std::map<std::string, long long> options; // tuning switches / read-back values (ss_set_option, ss_get_option)
 };
 
 namespace ss {
+
+inline long long option(const ss_ctx *ctx, const char *key, long long dflt) {
+    auto it = ctx->options.find(key);
+    return it == ctx->options.end() ? dflt : it->second;
+}
 
 inline ss_status fail(ss_ctx *ctx, ss_status code, const char *fmt, ...) {
     char buf[512];

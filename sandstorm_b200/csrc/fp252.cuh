@@ -49,6 +49,7 @@ SS_HD Fp r2() {
 
 // T[0..15] = a*b + p*2^256.  Operand scanning with two interleaved accumulators so that every
 // 32x32 product is one (lo,hi) pair on aligned limbs => ptxas emits one IMAD.WIDE.U32 per product.
+template <bool PLUS_P = true>
 SS_HD void mul_wide_plus_p(uint32_t (&T)[16], const Fp &a, const Fp &b) {
     using namespace ptx;
     uint32_t E[16], O[16];   // O[k] sits at limb position k+1
@@ -61,7 +62,7 @@ SS_HD void mul_wide_plus_p(uint32_t (&T)[16], const Fp &a, const Fp &b) {
         O[j] = (uint32_t)po;
         O[j + 1] = (uint32_t)(po >> 32);
     }
-    E[8] = SS_P0; E[9] = 0; E[10] = 0; E[11] = 0; E[12] = 0; E[13] = 0; E[14] = SS_P6; E[15] = SS_P7;
+    E[8] = PLUS_P ? SS_P0 : 0u; E[9] = 0; E[10] = 0; E[11] = 0; E[12] = 0; E[13] = 0; E[14] = PLUS_P ? SS_P6 : 0u; E[15] = PLUS_P ? SS_P7 : 0u;
 #pragma unroll
     for (int j = 8; j < 16; ++j) O[j] = 0;
 #pragma unroll

@@ -25,7 +25,7 @@ ss_status ss_poly_eval(ss_ctx *ctx, ss_field, const void *, uint64_t, int, int, 
 #endif
 
 #ifndef SS_HAVE_CONSTRAINTS
-ss_status ss_constraint_eval(ss_ctx *ctx, const void *, size_t, const void *, uint64_t, int, int, int, uint64_t, uint64_t, void *, void *) { return fail(ctx, SS_ERR_UNSUPPORTED, "ss_constraint_eval: not built"); }
+ss_status ss_constraint_eval(ss_ctx *ctx, const void *, size_t, const void *, uint64_t, int, int, int, uint64_t, uint64_t, int, void *, void *) { return fail(ctx, SS_ERR_UNSUPPORTED, "ss_constraint_eval: not built"); }
 #endif
 
 }

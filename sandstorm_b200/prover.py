@@ -7,7 +7,7 @@ ministark's prover runs them (steps 3-5, 8-10, 11-13, 15), for a layout of the r
     composition : constraint evaluation over the LDE coset -> coset iNTT -> ce interleaved columns
                   -> LDE -> Merkle commit                   [OOD point z drawn]
     OOD         : trace polynomials at z*g^offset for every tap, composition columns at z^ce
-    DEEP        : sum alpha^i (T(x) - y) / (x - z g^k) over the LDE coset          (src/lib.rs:102-116)
+    DEEP        : sum alpha^i (T(x) - y) / (x - z g^k) on the sub-coset 3<w_n>, extended to the LDE coset   (src/lib.rs:102-116)
     FRI         : per layer commit (rows of `fold` evaluations) -> alpha -> fold, until
                   layer_size / blowup <= max_remainder
     queries     : Merkle openings + rows at the query positions
@@ -59,6 +59,7 @@ class HotPathResult:
     ood_composition: list = field(default_factory=list)
     query_positions: list = field(default_factory=list)
     opened_bytes: int = 0
+    deep_matches_full_evaluation: bool | None = None
 
 
 class HotPathProver:
@@ -132,7 +133,7 @@ class HotPathProver:
         dist.all_gather_into_tensor(full, full[lo:lo + cnt].clone())
 
     # ---- the device stages ---------------------------------------------------------------------------------
-    def prove(self, base: Matrix, ext: Matrix, queries: bool = True) -> HotPathResult:
+    def prove(self, base: Matrix, ext: Matrix, queries: bool = True, self_check: bool = False) -> HotPathResult:
         """base / ext: the trace columns (every rank holds them: they come from the host-side trace builder).
         With world > 1 (torch.distributed initialised, one process per GPU): LDE and OOD are sharded by column,
         Merkle hashing / constraint evaluation / DEEP / FRI folds by LDE row range; LDE columns are broadcast
@@ -227,10 +228,21 @@ class HotPathProver:
         inv_x_minus_c(all_lde[self.v_col], _mont(zc), c)
         deep_prog = compile_program(deep_expr_shifted(t_terms, c_terms, self.u_col, self.v_col, self.g, P), self.log_n, b)
         del coeffs, comp_coeffs, comp_evals, work
+        # The quotient has degree < n - 1, so its n values on the sub-coset 3<w_n> — the LDE rows that are multiples of
+        # the blowup — determine it: evaluate only those (1/blowup of the work), then extend like any other column
+        # (coset iNTT of size n, zero padding, coset NTT of size N).  Same polynomial, hence the same N evaluations.
         deep = torch.empty((N, 4), dtype=torch.int64, device=dev)
-        evaluate(deep_prog, Matrix(all_lde, c), b, out=deep, rows=(row_lo, row_cnt) if world > 1 else None)
-        self._gather_rows(deep, row_lo, row_cnt)
+        sub_lo, sub_cnt = row_lo >> b, row_cnt >> b
+        evaluate(deep_prog, Matrix(all_lde, c), b, out=deep[:n], rows=(row_lo, sub_cnt) if world > 1 else None, log_row_step=b)
+        self._gather_rows(deep[:n], sub_lo, sub_cnt)
         self.mark("deep")
+        Matrix(deep[:n].view(1, n, 4), c).ntt_(inverse=True, coset=True)
+        deep[n:].zero_()
+        Matrix(deep.view(1, N, 4), c).ntt_(coset=True)
+        self.mark("deep_lde")
+        if self_check and world == 1:
+            # test hook: the extended quotient equals the row-by-row evaluation on the whole LDE coset
+            res.deep_matches_full_evaluation = bool(torch.equal(deep, evaluate(deep_prog, Matrix(all_lde, c), b)))
         # 13: FRI layers
         evals, log_size, offset = deep, self.log_n + b, 3
         layers = []

@@ -72,10 +72,10 @@ def test_rejects_malformed_programs(ss, oracle):
     c = ss.default_context()
     bad = bytearray(prog.blob)
     bad[0] ^= 0xFF
-    assert c.lib.ss_constraint_eval(c.handle, bytes(bad), len(bad), ctypes.c_void_p(d.data_ptr()), 16, 1, 3, 1, 0, 0, ctypes.c_void_p(out.data_ptr()), None) == -1
+    assert c.lib.ss_constraint_eval(c.handle, bytes(bad), len(bad), ctypes.c_void_p(d.data_ptr()), 16, 1, 3, 1, 0, 0, 0, ctypes.c_void_p(out.data_ptr()), None) == -1
     # wrong size / wrong log_n
-    assert c.lib.ss_constraint_eval(c.handle, prog.blob, len(prog.blob) - 32, ctypes.c_void_p(d.data_ptr()), 16, 1, 3, 1, 0, 0, ctypes.c_void_p(out.data_ptr()), None) == -1
-    assert c.lib.ss_constraint_eval(c.handle, prog.blob, len(prog.blob), ctypes.c_void_p(d.data_ptr()), 32, 1, 4, 1, 0, 0, ctypes.c_void_p(out.data_ptr()), None) == -1
+    assert c.lib.ss_constraint_eval(c.handle, prog.blob, len(prog.blob) - 32, ctypes.c_void_p(d.data_ptr()), 16, 1, 3, 1, 0, 0, 0, ctypes.c_void_p(out.data_ptr()), None) == -1
+    assert c.lib.ss_constraint_eval(c.handle, prog.blob, len(prog.blob), ctypes.c_void_p(d.data_ptr()), 32, 1, 4, 1, 0, 0, 0, ctypes.c_void_p(out.data_ptr()), None) == -1
 
 
 def test_deep_composition_matches_definition(ss, oracle):
@@ -190,3 +190,51 @@ def test_shifted_inverse_rewrite_is_equivalent(ss, oracle):
     shifted = evaluate(prog, m, 1)
     torch.cuda.synchronize()
     assert torch.equal(direct, shifted)
+
+
+@pytest.mark.parametrize("name,log_n", [("recursive", 13), ("starknet", 17)])
+def test_specialised_kernels_match_interpreter(ss, oracle, name, log_n):
+    """The build-time specialisations (tools/gen_ce_kernels.py) of the layout's composition and DEEP programs are
+    selected by structure hash — for any trace length and any challenge draw — and give bit-identical results to
+    the interpreter, which is itself checked against the tree evaluator above."""
+    import random
+
+    import torch
+
+    from sandstorm_b200.air import compile_program
+    from sandstorm_b200.air.deep import deep_expr_shifted
+    from sandstorm_b200.air.evaluate import evaluate
+    from sandstorm_b200.air.layouts import load_layout
+
+    P = oracle.P
+    L = load_layout(name)
+    C, ce = L.num_columns, 2
+    n, N = 1 << log_n, 2 << log_n
+    rnd = random.Random(log_n)
+    rng = np.random.default_rng(log_n)
+    cols = torch.from_numpy(oracle.random_felts(rng, C + ce + 3, N).view(np.int64)).cuda()
+    m = ss.Matrix(cols)
+    c = m.ctx
+    comp = compile_program(L.composition(n, inv_x_minus_one_col=C + ce), log_n, 1, [rnd.randrange(P) for _ in range(L.n_challenges())],
+                           [rnd.randrange(P) for _ in range(L.n_hints())], [rnd.randrange(P)])
+    g = pow(3, (P - 1) // n, P)
+    tt = [(col, off, rnd.randrange(P), rnd.randrange(P)) for col, off in L.taps()]
+    ct = [(C + j, rnd.randrange(P), rnd.randrange(P)) for j in range(ce)]
+    deep = compile_program(deep_expr_shifted(tt, ct, C + ce + 1, C + ce + 2, g, P), log_n, 1)
+    try:
+        for prog in (comp, deep):
+            c.check(c.lib.ss_set_option(c.handle, b"ce_aot", 0))
+            want = evaluate(prog, m, 1)
+            assert c.lib.ss_get_option(c.handle, b"ce_last_aot", -1) == 0
+            c.check(c.lib.ss_set_option(c.handle, b"ce_aot", 1))
+            got = evaluate(prog, m, 1)
+            assert c.lib.ss_get_option(c.handle, b"ce_last_aot", -1) == 1, "no specialised kernel matched the program's structure hash"
+            torch.cuda.synchronize()
+            assert torch.equal(want, got)
+            # a row range only (the multi-GPU path) writes exactly that range
+            part = torch.zeros_like(got)
+            evaluate(prog, m, 1, out=part, rows=(N // 4, N // 2))
+            torch.cuda.synchronize()
+            assert torch.equal(part[N // 4:3 * N // 4], want[N // 4:3 * N // 4]) and not part[:N // 4].any() and not part[3 * N // 4:].any()
+    finally:
+        c.check(c.lib.ss_set_option(c.handle, b"ce_aot", 1))

@@ -30,8 +30,10 @@ def test_hot_path_is_consistent(ss, oracle, layout, log_n):
     rng = np.random.default_rng(log_n)
     base = oracle.random_felts(rng, L.num_base_columns, 1 << log_n)
     ext = oracle.random_felts(rng, L.num_extension_columns, 1 << log_n)
-    res = hp.prove(ss.Matrix.from_numpy(base), ss.Matrix.from_numpy(ext))
+    res = hp.prove(ss.Matrix.from_numpy(base), ss.Matrix.from_numpy(ext), self_check=True)
     torch.cuda.synchronize()
+    # the DEEP quotient, evaluated on the sub-coset 3<w_n> and extended, equals its evaluation on every LDE row
+    assert res.deep_matches_full_evaluation is True
     # commitments
     assert res.roots["base"] == oracle.merkle_build(oracle.TREE_KECCAK_M20, oracle.lde(base, 1))[2]
     assert res.roots["ext"] == oracle.merkle_build(oracle.TREE_KECCAK_M20, oracle.lde(ext, 1))[2]

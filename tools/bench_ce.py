@@ -40,7 +40,11 @@ def main():
     lde[:, :, 3] &= (1 << 58) - 1
     m = ss.Matrix(lde)
     out = torch.empty((N, 4), dtype=torch.int64, device="cuda")
-    for name, prog in (("composition", comp), ("deep", deep)):
+    c = m.ctx
+    variants = [int(v) for v in os.environ.get("SS_GEN_MINB_VARIANTS", "0").split(",")]
+    for name, prog, aot, mb in [(nm, pg, a, v) for nm, pg in (("composition", comp), ("deep", deep)) for a, v in [(0, 0)] + [(1, v) for v in variants]]:
+        c.check(c.lib.ss_set_option(c.handle, b"ce_aot", aot))
+        c.check(c.lib.ss_set_option(c.handle, b"ce_aot_minb", mb))
         for _ in range(2):
             evaluate(prog, m, log_b, out=out)
         torch.cuda.synchronize()
@@ -52,7 +56,7 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
-        rec = {"program": name, "minb": os.environ.get("SS_CE_MINB", "default"), "log_n": log_n, "rows": N, "ms": round(ms, 3), "ns_per_row": round(ms * 1e6 / N, 3),
+        rec = {"program": name, "aot": int(c.lib.ss_get_option(c.handle, b"ce_last_aot", -1)), "aot_minb": mb, "log_n": log_n, "rows": N, "ms": round(ms, 3), "ns_per_row": round(ms * 1e6 / N, 3),
                "words": prog.n_instr, "n_mul": prog.n_mul, "n_addsub": prog.n_addsub, "n_red": prog.n_red, "n_dot": prog.n_dot, "taps": prog.n_trace_taps,
                "slots": prog.n_slots, "compile_s": round(t_compile, 1), "mul_per_s": prog.n_mul * N / (ms * 1e-3)}
         print(json.dumps(rec), flush=True)
