@@ -153,6 +153,15 @@ ss_status ss_inv_x_minus_c(ss_ctx *ctx, ss_field field, int log_n, const void *h
 ss_status ss_poly_eval(ss_ctx *ctx, ss_field field, const void *d_coeffs, uint64_t coeff_stride, int log_n, int natural_order,
                        const int32_t *h_cols, const void *h_points, size_t n_evals, void *h_out);
 
+/* The same out-of-domain values computed from the TRACE evaluations (barycentric form; no coefficient vectors):
+ * h_out[e] = T_{h_cols[e]}(z * g^h_offsets[e]) with g the generator of the trace domain and d_trace_cols the
+ * column-major trace (n = 2^log_n rows, natural order) — the mask of air.trace_arguments() (ministark).
+ * row_count != 0 restricts the sum to the trace rows [row_begin, row_begin + row_count): the results of disjoint
+ * ranges add up to the value (one range per GPU).  z must lie outside the trace domain.  Synchronises. */
+ss_status ss_ood_eval(ss_ctx *ctx, ss_field field, const void *d_trace_cols, uint64_t col_stride, int log_n,
+                      const int32_t *h_cols, const uint64_t *h_offsets, size_t n_evals, const void *h_z,
+                      uint64_t row_begin, uint64_t row_count, void *h_out);
+
 /* ------------------------------------------------------------------ constraint evaluation (§8 a4-a7)
  * Evaluates a compiled composition-constraint program (the Expr DAG of
  * AirConfig::composition_constraint, layouts/src/recursive/air.rs:1184-1200, flattened by the host

@@ -14,6 +14,7 @@
 // adjacent-pair folds  b[m] = a[2m] + w^(n/2) a[2m+1],  c[m] = b[2m] + w^(n/4) b[2m+1], ...
 #include "ctx.h"
 #include "fp252.cuh"
+#include <algorithm>
 
 using namespace ss;
 
@@ -158,6 +159,127 @@ __global__ void __launch_bounds__(128) inv_x_minus_c_kernel(Fp *out, int log_n, 
     }
 }
 
+// ---- out-of-domain evaluation from the trace itself (barycentric form) ------------------------------------
+// With g the generator of the trace domain (order n) and t_j = T(g^j) the trace column,
+//     T(z g^k) = (z^n - 1)/n * sum_j t_{(j+k) mod n} * W_j,      W_j = g^j / (z - g^j) = 1 / (z g^-j - 1):
+// every tap (column, row offset k) of the AIR is a dot product of the SAME weight vector with a rotated
+// column, so the step needs no coefficient vectors, every multiplication is a multiply-accumulate into an
+// unreduced 512-bit sum (fp::WideAcc, one Montgomery reduction per thread), and — unlike Horner — the sum
+// splits over row ranges (one per GPU).
+//
+// bary_weights_kernel: W_j for j in [row_begin, row_begin + count), Montgomery batch inversion per thread.
+__global__ void __launch_bounds__(128) bary_weights_kernel(Fp *out, unsigned long long row_begin, unsigned long long count, Fp z,
+                                                             const Fp *ginv_lo, const Fp *ginv_hi) {
+    const unsigned long long chunk = (unsigned long long)blockDim.x * INV_ROWS;
+    const unsigned long long base = blockIdx.x * chunk + threadIdx.x;
+    Fp d[INV_ROWS], pre[INV_ROWS];
+    Fp acc = fp::one();
+#pragma unroll
+    for (int k = 0; k < INV_ROWS; ++k) {
+        const unsigned long long t = base + (unsigned long long)k * blockDim.x;
+        Fp x = fp::one();
+        if (t < count) {
+            const unsigned long long j = row_begin + t;
+            x = ld_fp(ginv_lo + (j & 4095ull));
+            if (j >> 12) x = fp::mul(x, ld_fp(ginv_hi + (j >> 12)));
+            x = fp::sub(fp::mul(x, z), fp::one());
+        }
+        d[k] = x;
+        pre[k] = acc;
+        acc = fp::mul(acc, x);
+    }
+    auto sqn = [](Fp v, int m) { for (int t = 0; t < m; ++t) v = fp::sqr(v); return v; };
+    const Fp e2 = fp::mul(sqn(acc, 1), acc), e4 = fp::mul(sqn(e2, 2), e2), e8 = fp::mul(sqn(e4, 4), e4);
+    const Fp e16 = fp::mul(sqn(e8, 8), e8), e32 = fp::mul(sqn(e16, 16), e16), e64 = fp::mul(sqn(e32, 32), e32);
+    const Fp e128 = fp::mul(sqn(e64, 64), e64), e192 = fp::mul(sqn(e128, 64), e64);
+    const Fp gq = fp::mul(e192, acc);
+    Fp inv = fp::mul(sqn(fp::mul(sqn(gq, 55), gq), 4), e192);
+#pragma unroll
+    for (int k = INV_ROWS - 1; k >= 0; --k) {
+        const unsigned long long t = base + (unsigned long long)k * blockDim.x;
+        const Fp r = fp::mul(inv, pre[k]);
+        inv = fp::mul(inv, d[k]);
+        if (t < count) st_fp(out + t, fp::canon(r));
+    }
+}
+
+// ood_dot_kernel: block (x = tap pair, y = row chunk) accumulates  sum_j t[(j + off) mod n] * W_j  over its chunk
+// for two taps of one column (the weight is loaded once for both) and writes one partial per tap.  Taps vary
+// fastest over the grid, so the CTAs in flight share a few chunks: their weights and column windows stay in L2.
+constexpr int OOD_THREADS = 128;
+constexpr int OOD_ROWS = 32;                            // rows per thread
+constexpr int OOD_CHUNK = OOD_THREADS * OOD_ROWS;       // rows per block
+struct OodTap { int col; unsigned int off0, off1; int n_taps; };   // one column, one or two row offsets
+
+__global__ void __launch_bounds__(OOD_THREADS) ood_dot_kernel(const Fp *__restrict__ cols, unsigned long long stride, int log_n,
+                                                               const Fp *__restrict__ weights, unsigned long long row_begin,
+                                                               unsigned long long count, const OodTap *__restrict__ taps, unsigned int n_pairs,
+                                                               unsigned int n_chunks, Fp *__restrict__ partials) {
+    __shared__ Fp sm[2][OOD_THREADS];
+    const unsigned int pair = blockIdx.x % n_pairs, chunk = blockIdx.x / n_pairs;      // tap pairs vary fastest
+    const OodTap tp = taps[pair];
+    const unsigned long long mask = (1ull << log_n) - 1;
+    const Fp *col = cols + (unsigned long long)tp.col * stride;
+    const unsigned long long base = (unsigned long long)chunk * OOD_CHUNK + threadIdx.x;
+    fp::WideAcc a0, a1;
+    fp::acc_init(a0);
+    fp::acc_init(a1);
+    if (tp.n_taps == 2) {
+#pragma unroll 1
+        for (int k = 0; k < OOD_ROWS; ++k) {
+            const unsigned long long t = base + (unsigned long long)k * OOD_THREADS;
+            if (t < count) {
+                const unsigned long long j = row_begin + t;
+                const Fp w = ld_fp(weights + t);
+                fp::acc_mac(a0, ld_fp(col + ((j + tp.off0) & mask)), w);
+                fp::acc_mac(a1, ld_fp(col + ((j + tp.off1) & mask)), w);
+            }
+        }
+    } else {
+#pragma unroll 1
+        for (int k = 0; k < OOD_ROWS; ++k) {
+            const unsigned long long t = base + (unsigned long long)k * OOD_THREADS;
+            if (t < count) fp::acc_mac(a0, ld_fp(col + ((row_begin + t + tp.off0) & mask)), ld_fp(weights + t));
+        }
+    }
+    // Montgomery-reduce the thread sums (linear: R^-1 * sum), then a shared-memory tree of modular additions
+    Fp r0 = fp::acc_reduce(a0), r1 = fp::acc_reduce(a1);
+    fp::cond_sub_4p(r0); fp::cond_sub_2p(r0);
+    fp::cond_sub_4p(r1); fp::cond_sub_2p(r1);
+    sm[0][threadIdx.x] = r0;
+    sm[1][threadIdx.x] = r1;
+    __syncthreads();
+    for (int active = OOD_THREADS / 2; active >= 1; active >>= 1) {
+        if ((int)threadIdx.x < active) {
+            sm[0][threadIdx.x] = fp::add(sm[0][threadIdx.x], sm[0][threadIdx.x + active]);
+            sm[1][threadIdx.x] = fp::add(sm[1][threadIdx.x], sm[1][threadIdx.x + active]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        Fp *dst = partials + ((unsigned long long)pair * n_chunks + chunk) * 2;
+        st_fp(dst, sm[0][0]);
+        st_fp(dst + 1, sm[1][0]);
+    }
+}
+
+// ood_finish_kernel: block e sums the partials of evaluation e over the chunks and scales by (z^n - 1)/n
+__global__ void __launch_bounds__(256) ood_finish_kernel(const Fp *__restrict__ partials, unsigned int n_chunks, const int2 *__restrict__ where,
+                                                          Fp scale, Fp *__restrict__ out) {
+    __shared__ Fp sm[256];
+    const int2 w = where[blockIdx.x];                      // (tap pair, slot 0/1)
+    const Fp *src = partials + (unsigned long long)w.x * n_chunks * 2 + w.y;
+    Fp acc = fp::zero();
+    for (unsigned int c = threadIdx.x; c < n_chunks; c += 256) acc = fp::add(acc, ld_fp(src + 2ull * c));
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int active = 128; active >= 1; active >>= 1) {
+        if ((int)threadIdx.x < active) sm[threadIdx.x] = fp::add(sm[threadIdx.x], sm[threadIdx.x + active]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) st_fp(out + blockIdx.x, fp::canon(fp::mul(sm[0], scale)));
+}
+
 void fill_x_lo(Fp *dst, size_t n, int log_n, int h) {
     Fp w = fp::one();
     {   // w_N
@@ -257,6 +379,83 @@ ss_status ss_inv_x_minus_c(ss_ctx *ctx, ss_field field, int log_n, const void *h
     inv_x_minus_c_kernel<<<(unsigned)((n + chunk - 1) / chunk), 128, 0, pick_stream(ctx, stream)>>>(static_cast<Fp *>(d_out), log_n, fp::canon(load_host(h_c)), lo, hi);
     ctx->launches++;
     SS_CUDA_CHECK(ctx, cudaGetLastError());
+    return SS_OK;
+}
+
+ss_status ss_ood_eval(ss_ctx *ctx, ss_field field, const void *d_trace_cols, uint64_t col_stride, int log_n,
+                      const int32_t *h_cols, const uint64_t *h_offsets, size_t n_evals, const void *h_z,
+                      uint64_t row_begin, uint64_t row_count, void *h_out) {
+    if (!ctx) return SS_ERR_INVALID;
+    if (field != SS_FIELD_FP252) return fail(ctx, SS_ERR_UNSUPPORTED, "ss_ood_eval: field %d not built", (int)field);
+    if (!d_trace_cols || log_n < 0 || log_n > 32 || !h_z || (n_evals && (!h_cols || !h_offsets || !h_out)) || col_stride < (1ull << log_n))
+        return fail(ctx, SS_ERR_INVALID, "ss_ood_eval: bad arguments");
+    if (n_evals == 0) return SS_OK;
+    const unsigned long long n = 1ull << log_n;
+    if (row_count == 0) { row_begin = 0; row_count = n; }
+    if (row_begin + row_count > n) return fail(ctx, SS_ERR_INVALID, "ss_ood_eval: row range outside the trace domain");
+    SS_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+    // pair up the taps of each column (the weight vector is read once per pair)
+    std::vector<size_t> order(n_evals);
+    for (size_t e = 0; e < n_evals; ++e) {
+        if (h_cols[e] < 0 || h_offsets[e] >= n) return fail(ctx, SS_ERR_INVALID, "ss_ood_eval: bad tap %zu", e);
+        order[e] = e;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return h_cols[a] < h_cols[b]; });
+    std::vector<OodTap> taps;
+    std::vector<int2> where(n_evals);
+    for (size_t k = 0; k < n_evals;) {
+        const size_t e0 = order[k];
+        OodTap t{h_cols[e0], (unsigned int)h_offsets[e0], 0u, 1};
+        where[e0] = make_int2((int)taps.size(), 0);
+        if (k + 1 < n_evals && h_cols[order[k + 1]] == h_cols[e0]) {
+            const size_t e1 = order[k + 1];
+            t.off1 = (unsigned int)h_offsets[e1];
+            t.n_taps = 2;
+            where[e1] = make_int2((int)taps.size(), 1);
+            k += 2;
+        } else {
+            k += 1;
+        }
+        taps.push_back(t);
+    }
+    // (z^n - 1) / n on the host (log n squarings, one inversion of a small integer)
+    const Fp z = fp::canon(load_host(h_z));
+    Fp zn = z;
+    for (int s2 = 0; s2 < log_n; ++s2) zn = fp::sqr(zn);
+    Fp n_field = fp::one();
+    for (int s2 = 0; s2 < log_n; ++s2) n_field = fp::add(n_field, n_field);
+    const Fp scale = fp::canon(fp::mul(fp::sub(zn, fp::one()), fp::inv(n_field)));
+    // powers of g^-1 (g = generator of the trace domain): lo[j] = g^-j, j < 4096; hi[j] = g^-(4096 j)
+    Fp *lo, *hi;
+    ss_status rc;
+    if ((rc = cached_table(ctx, {24, log_n, 0}, n < 4096 ? n : 4096,
+                           [](Fp *d, size_t m, int ln, int) { const Fp w = host_root_of_unity(ln, true); Fp c = fp::one(); for (size_t i = 0; i < m; ++i) { d[i] = fp::canon(c); c = fp::mul(c, w); } }, &lo))) return rc;
+    if ((rc = cached_table(ctx, {25, log_n, 0}, n <= 4096 ? 1 : n / 4096,
+                           [](Fp *d, size_t m, int ln, int) { const Fp w = fp::pow_u64(host_root_of_unity(ln, true), 4096); Fp c = fp::one(); for (size_t i = 0; i < m; ++i) { d[i] = fp::canon(c); c = fp::mul(c, w); } }, &hi))) return rc;
+    const unsigned int n_chunks = (unsigned int)((row_count + OOD_CHUNK - 1) / OOD_CHUNK);
+    Fp *d_w = nullptr, *d_part = nullptr, *d_out = nullptr;
+    OodTap *d_taps = nullptr;
+    int2 *d_where = nullptr;
+    cudaError_t ce = cudaMalloc(&d_w, row_count * sizeof(Fp));
+    if (ce == cudaSuccess) ce = cudaMalloc(&d_part, taps.size() * (size_t)n_chunks * 2 * sizeof(Fp));
+    if (ce == cudaSuccess) ce = cudaMalloc(&d_out, n_evals * sizeof(Fp));
+    if (ce == cudaSuccess) ce = cudaMalloc(&d_taps, taps.size() * sizeof(OodTap));
+    if (ce == cudaSuccess) ce = cudaMalloc(&d_where, n_evals * sizeof(int2));
+    auto cleanup = [&] { cudaFree(d_w); cudaFree(d_part); cudaFree(d_out); cudaFree(d_taps); cudaFree(d_where); };
+    if (ce != cudaSuccess) { cleanup(); return fail(ctx, SS_ERR_OOM, "ss_ood_eval: %s", cudaGetErrorString(ce)); }
+    cudaMemcpy(d_taps, taps.data(), taps.size() * sizeof(OodTap), cudaMemcpyHostToDevice);
+    cudaMemcpy(d_where, where.data(), n_evals * sizeof(int2), cudaMemcpyHostToDevice);
+    const unsigned long long wchunk = 128ull * INV_ROWS;
+    bary_weights_kernel<<<(unsigned)((row_count + wchunk - 1) / wchunk), 128>>>(d_w, row_begin, row_count, z, lo, hi);
+    if ((unsigned long long)taps.size() * n_chunks > 0x7fffffffull) { cleanup(); return fail(ctx, SS_ERR_UNSUPPORTED, "ss_ood_eval: grid too large"); }
+    ood_dot_kernel<<<(unsigned)(taps.size() * n_chunks), OOD_THREADS>>>(static_cast<const Fp *>(d_trace_cols), col_stride, log_n, d_w, row_begin,
+                                                                           row_count, d_taps, (unsigned)taps.size(), n_chunks, d_part);
+    ood_finish_kernel<<<(unsigned)n_evals, 256>>>(d_part, n_chunks, d_where, scale, d_out);
+    ctx->launches += 3;
+    ce = cudaGetLastError();
+    if (ce == cudaSuccess) ce = cudaMemcpy(h_out, d_out, n_evals * sizeof(Fp), cudaMemcpyDeviceToHost);
+    cleanup();
+    if (ce != cudaSuccess) return fail(ctx, SS_ERR_CUDA, "ss_ood_eval: %s", cudaGetErrorString(ce));
     return SS_OK;
 }
 

@@ -121,6 +121,22 @@ def poly_eval(coeffs: "Matrix", cols, points_mont: np.ndarray, natural_order: bo
     return out
 
 
+def ood_eval(trace: "Matrix", cols, offsets, z_mont: np.ndarray, rows: tuple[int, int] | None = None) -> np.ndarray:
+    """Out-of-domain values from the trace evaluations (ss_ood_eval, barycentric form): returns uint64[len, 4] with
+    T_{cols[e]}(z * g^offsets[e]) in Montgomery limbs.  rows = (begin, count) restricts the sum to that range of trace
+    rows: the results of disjoint ranges add up (mod p) to the value."""
+    ctx = trace.ctx
+    cols = np.ascontiguousarray(cols, dtype=np.int32)
+    offs = np.ascontiguousarray([int(o) % trace.num_rows for o in offsets], dtype=np.uint64)
+    out = np.zeros((len(cols), 4), dtype=np.uint64)
+    begin, count = rows if rows is not None else (0, 0)
+    torch.cuda.current_stream().synchronize()
+    ctx.check(ctx.lib.ss_ood_eval(ctx.handle, _lib.FIELD_FP252, ctypes.c_void_p(trace.data.data_ptr()), trace.num_rows, trace.log_rows,
+                                  cols.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), offs.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), len(cols),
+                                  _felt_bytes(z_mont), begin, count, out.ctypes.data_as(ctypes.c_void_p)))
+    return out
+
+
 def inv_x_minus_c(out: torch.Tensor, c_mont: np.ndarray, ctx: Context | None = None) -> torch.Tensor:
     """out[i] = 1 / (3 * w_N^i - c) for the N = out.shape[0] points of the LDE coset (ss_inv_x_minus_c)."""
     ctx = ctx or default_context(out.device.index)

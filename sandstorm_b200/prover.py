@@ -30,7 +30,7 @@ from .air.deep import deep_expr_shifted
 from .air.evaluate import evaluate
 from .air.expr import P
 from .air.layouts import load_layout
-from .matrix import Matrix, fri_fold, inv_x_minus_c, poly_eval
+from .matrix import Matrix, fri_fold, inv_x_minus_c, ood_eval, poly_eval
 
 R = 2**256
 
@@ -153,12 +153,11 @@ class HotPathProver:
         # one matrix for every committed column: trace | composition (ce) | w | u | v  (see __init__)
         all_lde = torch.empty((C + self.ce + 3, N, 4), dtype=torch.int64, device=dev)
         lde = all_lde[:C]
-        coeffs = torch.empty((C, n, 4), dtype=torch.int64, device=dev)      # only the owned columns are filled
 
         def lde_cols(src: Matrix, first_col: int):
             for j in owned_columns(src.num_cols, rank, world):
                 c.check(c.lib.ss_lde(c.handle, _lib.FIELD_FP252, ctypes.c_void_p(src.data[j].data_ptr()), n, 1, self.log_n, b,
-                                     ctypes.c_void_p(lde[first_col + j].data_ptr()), N, ctypes.c_void_p(coeffs[first_col + j].data_ptr()), n,
+                                     ctypes.c_void_p(lde[first_col + j].data_ptr()), N, None, n,
                                      _lib.ORDER_NATURAL, None))
 
         # 3-5: base trace
@@ -195,28 +194,33 @@ class HotPathProver:
         self.mark("ntt_comp_fwd")
         res.roots["composition"], h = self._commit(comp_lde.data_ptr(), N, self.ce, self.log_n + b); handles.append(h)
         self.mark("merkle_comp")
-        # 11: out-of-domain evaluations (each rank evaluates the taps of the columns whose coefficients it holds)
+        # 11: out-of-domain evaluations of every tap, straight from the trace (barycentric dot products with one shared
+        #     weight vector, ss_ood_eval).  Each rank sums over its range of trace rows; the partial values add up.
         z = self._draw()
         taps = L.taps()
-        pts = [z * pow(self.g, off, P) % P for _, off in taps]
-
-        def owner(col):
-            return (col % world) if col < nb else ((col - nb) % world)
-
-        mine = [k for k, (col, _) in enumerate(taps) if owner(col) == rank]
-        ood = torch.zeros((len(taps), 4), dtype=torch.int64, device=dev)
-        if mine:
-            vals = poly_eval(Matrix(coeffs, c), [taps[k][0] for k in mine], np.stack([_mont(pts[k]) for k in mine]))
-            ood[torch.tensor(mine, device=dev)] = torch.from_numpy(vals.view(np.int64)).to(dev)
+        t_lo, t_cnt = rank * (n // world), n // world
+        parts = np.zeros((len(taps), 4), dtype=np.uint64)
+        for mat, first, count in ((base, 0, nb), (ext, nb, C - nb)):
+            idx = [k for k, (col, _) in enumerate(taps) if first <= col < first + count]
+            if idx:
+                parts[idx] = ood_eval(mat, [taps[k][0] - first for k in idx], [taps[k][1] for k in idx], _mont(z),
+                                      rows=(t_lo, t_cnt) if world > 1 else None)
+        to_int = lambda a: [int(r[0]) | int(r[1]) << 64 | int(r[2]) << 128 | int(r[3]) << 192 for r in a]
         if world > 1:
             import torch.distributed as dist
 
-            dist.all_reduce(ood)                  # exactly one rank contributes each row, the others add zeros
+            mine = torch.from_numpy(parts.view(np.int64)).to(dev)
+            every = torch.empty((world,) + tuple(mine.shape), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(every, mine)
+            per_rank = [to_int(a) for a in every.cpu().numpy().view(np.uint64)]
+            ood_m = [sum(vals) % P for vals in zip(*per_rank)]
+        else:
+            ood_m = to_int(parts)
         zc = pow(z, self.ce, P)
         ood_c = poly_eval(Matrix(comp_coeffs, c), list(range(self.ce)), np.stack([_mont(zc)] * self.ce), natural_order=True)
         self.mark("ood")
-        from_m = lambda a: [(int(r[0]) | int(r[1]) << 64 | int(r[2]) << 128 | int(r[3]) << 192) * pow(R, -1, P) % P for r in a]
-        res.ood_trace, res.ood_composition = from_m(ood.cpu().numpy().view(np.uint64)), from_m(ood_c)
+        rinv = pow(R, -1, P)
+        res.ood_trace, res.ood_composition = [v * rinv % P for v in ood_m], [v * rinv % P for v in to_int(ood_c)]
         # 12: DEEP composition over the LDE coset (coefficients = powers of one alpha, src/lib.rs:102-116)
         alpha = self._draw()
         t_terms, c_terms, k = [], [], 0
@@ -227,7 +231,7 @@ class HotPathProver:
         inv_x_minus_c(all_lde[self.u_col], _mont(z), c)
         inv_x_minus_c(all_lde[self.v_col], _mont(zc), c)
         deep_prog = compile_program(deep_expr_shifted(t_terms, c_terms, self.u_col, self.v_col, self.g, P), self.log_n, b)
-        del coeffs, comp_coeffs, comp_evals, work
+        del comp_coeffs, comp_evals, work
         # The quotient has degree < n - 1, so its n values on the sub-coset 3<w_n> — the LDE rows that are multiples of
         # the blowup — determine it: evaluate only those (1/blowup of the work), then extend like any other column
         # (coset iNTT of size n, zero padding, coset NTT of size N).  Same polynomial, hence the same N evaluations.

@@ -76,3 +76,35 @@ def test_ood_values_match_horner(ss, oracle):
         want.append(acc)
     assert oracle.from_mont(poly_eval(coeffs, [0, 1], oracle.to_mont([z, z]))) == want
     assert oracle.from_mont(poly_eval(ss.Matrix.from_numpy(plain), [0, 1], oracle.to_mont([z, z]), natural_order=True)) == want
+
+
+@pytest.mark.parametrize("log_n", [3, 9, 13])
+def test_barycentric_ood_matches_horner(ss, oracle, log_n):
+    """ss_ood_eval (dot products of the trace with the barycentric weights) against Horner evaluation of the
+    oracle's interpolation, for wrapped and unwrapped row offsets, whole domain and row ranges that add up."""
+    from sandstorm_b200.matrix import ood_eval
+
+    P = oracle.P
+    n = 1 << log_n
+    rng = np.random.default_rng(60 + log_n)
+    cols = oracle.random_felts(rng, 3, n)
+    coeffs = [oracle.from_mont(c) for c in oracle.ntt(cols, inverse=True)]
+    z = int.from_bytes(rng.bytes(31), "big")
+    g = pow(3, (P - 1) >> log_n, P)
+    taps = [(0, 0), (0, 1), (0, n - 1), (1, 2 % n), (1, n // 2), (2, 5 % n), (2, 0), (2, 1), (2, 3 % n), (0, n + 1)]
+
+    def horner(c, x):
+        acc = 0
+        for v in reversed(coeffs[c]):
+            acc = (acc * x + v) % P
+        return acc
+
+    want = [horner(c, z * pow(g, off, P) % P) for c, off in taps]
+    m = ss.Matrix.from_numpy(cols)
+    zm = oracle.to_mont([z])[0]
+    got = oracle.from_mont(ood_eval(m, [c for c, _ in taps], [off for _, off in taps], zm))
+    assert got == want
+    if n >= 8:
+        cuts = [0, n // 8, n // 2 + 1, n]
+        parts = [oracle.from_mont(ood_eval(m, [c for c, _ in taps], [off for _, off in taps], zm, rows=(a, b - a))) for a, b in zip(cuts, cuts[1:])]
+        assert [sum(v) % P for v in zip(*parts)] == want
