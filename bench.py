@@ -52,6 +52,7 @@ def lde_ops(n_cols: int, log_n: int) -> float:
 
 
 NTT_LOG_TILE = 11                           # csrc/ntt_fp252.cuh SS_NTT_LOG_TILE
+MUL_PEAK = 592 * 1.965e9 / 275 * 32         # Fp252 multiplications/s if the IMAD pipe did nothing else (tools/ubench/bfly.cu)
 
 
 def plan_passes(log_n: int) -> int:
@@ -317,10 +318,11 @@ class FullHotPath(HotPath):
         self.compile_s = time.perf_counter() - t0
         self.events = self.prover.timeline
         self.last = None
+        self.column_ready = None
 
     def step(self):
         ss = self.ss
-        self.last = self.prover.prove(ss.Matrix(self.base, self.ctx), ss.Matrix(self.ext, self.ctx))
+        self.last = self.prover.prove(ss.Matrix(self.base, self.ctx), ss.Matrix(self.ext, self.ctx), column_ready=self.column_ready)
         return []
 
     def free(self, trees):
@@ -437,10 +439,28 @@ def gpu_arm(args):
         h_base.copy_(hp.base); h_ext.copy_(hp.ext)
         h2d = h_base.numel() * 8 + h_ext.numel() * 8
 
+        copy_stream = torch.cuda.Stream()
+        n_trace_cols = hp.base.shape[0] + hp.ext.shape[0]
+
         def e2e_step():
-            hp.base.copy_(h_base, non_blocking=True)
-            hp.ext.copy_(h_ext, non_blocking=True)
+            # the trace is uploaded column by column on a copy stream; the LDE of column k waits only for column k,
+            # so the rest of the H2D traffic overlaps the first LDE stage
+            main = torch.cuda.current_stream()
+            copy_stream.wait_stream(main)                  # the previous step has finished reading the buffers
+            events = []
+            with torch.cuda.stream(copy_stream):
+                for k in range(n_trace_cols):
+                    dst, src = (hp.base[k], h_base[k]) if k < hp.base.shape[0] else (hp.ext[k - hp.base.shape[0]], h_ext[k - hp.base.shape[0]])
+                    dst.copy_(src, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(copy_stream)
+                    events.append(ev)
+            if isinstance(hp, FullHotPath):
+                hp.column_ready = lambda k: main.wait_stream(copy_stream) if k is None else main.wait_event(events[k])
+            else:
+                main.wait_stream(copy_stream)
             trees = hp.step()
+            main.wait_stream(copy_stream)
             roots = [tr.root() for tr in trees]    # D2H of each 32-byte root (+ sub-root all-gather at N > 1)
             hp.free(trees)                         # (the full prover reads its roots, OOD values and openings itself)
             return roots
@@ -480,6 +500,26 @@ def gpu_arm(args):
     tp = os.path.join(ROOT, "profiles", "ntt_pass_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    # dominant kernel of the step: the composition-constraint evaluation (one launch per step; its stage is the launch)
+    roofline = None
+    if isinstance(hp, FullHotPath) and stages.get("constraint_eval"):
+        ce_ms = stages["constraint_eval"]
+        n_cols_read = N_BASE + N_EXT + 1                                   # trace columns + the w = 1/(x-1) column
+        rows = hp.N // world
+        algo = 32.0 * (n_cols_read + 1) * rows                              # every column element once + one output per row
+        ce_ach = algo / (ce_ms * 1e-3) / 1e9
+        ce_traffic = None
+        cp = os.path.join(ROOT, "profiles", "ce_kernel_traffic.json")
+        if os.path.exists(cp):
+            t = json.load(open(cp))
+            ce_traffic = t["dram_bytes_per_row"] * rows
+        muls = hp.program.n_mul * rows / (ce_ms * 1e-3)
+        roofline = {"bound": "hbm", "kernel": "ce_gen_starknet_composition (ss_constraint_eval)", "achieved": ce_ach, "peak": peak, "unit": "GB/s",
+                    "frac": ce_ach / peak, "traffic": ce_traffic, "peak_source": peak_src, "launch_ms": ce_ms,
+                    "algorithmic_bytes_per_row": 32 * (n_cols_read + 1),
+                    "field_muls_per_s": muls, "field_mul_pipe_peak_per_s": MUL_PEAK, "field_mul_pipe_frac": muls / MUL_PEAK,
+                    "note": "arithmetic-bound: %d Montgomery multiplications + %d add/sub per row on 384 algorithmic bytes; the integer pipe, not HBM, is the roof "
+                            "(mul peak = 592 SMSPs x 1.965 GHz / 275 cycles per warp-multiplication, profiles/r01_ntt_tile_ab.md)" % (hp.program.n_mul, hp.program.n_addsub)}
     cpu_val, cpu_info = (None, {})
     if not args.no_cpu and world >= 1:
         cpu_val, cpu_info = cpu_oracle_run(2, 1)
@@ -488,7 +528,7 @@ def gpu_arm(args):
         "ms_per_step": ms_per_step, "prove_seconds": ms_per_step / 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u256 (Fp252 Montgomery, 8 x u32 limbs)", "data": "synthetic",
         "config": {"workload": f"starknet layout, 2^{log_n - CYCLE_HEIGHT_LOG} Cairo steps (n=2^{log_n} rows, LDE 2^{log_n + LOG_BLOWUP}), Fp252, {N_BASE}+{N_EXT} trace + {N_COMP} composition columns, masked-Keccak Merkle",
-                   "requested_log_steps": args.log_steps, "parallelism": f"{world} rank(s): LDE + OOD sharded by column (NCCL broadcast / all-reduce), Merkle + constraint eval + DEEP + FRI folds by LDE row range (all-gather, combined sub-roots); composition-column NTTs replicated", "l2": "inputs_larger_than_L2",
+                   "requested_log_steps": args.log_steps, "parallelism": f"{world} rank(s): LDE sharded by column (NCCL broadcast), Merkle + constraint eval + DEEP + FRI folds by LDE row range and OOD by trace row range (all-gather, combined sub-roots / summed partial values); composition-column and DEEP-extension NTTs replicated", "l2": "inputs_larger_than_L2",
                    "stages_in_step": list(stages.keys()),
                    "not_in_step": [] if isinstance(hp, FullHotPath) else ["constraint_eval (stand-in column)", "ood", "deep_composition", "fri_layers", "queries"],
                    "air": "starknet layout, 195 constraints (sandstorm_b200/air/layouts/starknet.json)" if isinstance(hp, FullHotPath) else None,
@@ -496,9 +536,10 @@ def gpu_arm(args):
         "stages_ms": {k: round(v, 3) for k, v in stages.items()},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "ss::ntt_pass_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src,
-                     "note": "Fp252 NTT is bound by the carry-chained IMAD.WIDE pipe, not HBM (profiles/r01_pipe_microbench.md)"},
+        "roofline": roofline,
+        "roofline_ntt": {"bound": "hbm", "kernel": "ss::ntt_pass_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "note": "Fp252 NTT is bound by the carry-chained IMAD.WIDE pipe, not HBM (profiles/r01_pipe_microbench.md)"},
         "cpu_baseline": {"value": cpu_val, "unit": "field-ops/s", "cores": cpu_info.get("cores"), "kind": "port", "sample": cpu_info.get("sample")},
     }
     if e2e:

@@ -20,6 +20,38 @@ ss_status scratch_reserve(ss_ctx *ctx, size_t bytes, void **out) {
     return SS_OK;
 }
 
+cudaError_t dev_alloc(ss_ctx *ctx, void **out, size_t bytes) {
+    const size_t want = (bytes + (1u << 20) - 1) & ~(size_t)((1u << 20) - 1);     // 1 MiB granules: sizes repeat exactly
+    auto it = ctx->pool_free.lower_bound(want);
+    if (it != ctx->pool_free.end() && it->first <= want + want / 8) {             // reuse a block at most 12.5 % larger
+        *out = it->second;
+        ctx->pool_free.erase(it);
+        return cudaSuccess;
+    }
+    cudaError_t e = cudaMalloc(out, want);
+    if (e == cudaErrorMemoryAllocation) {                                            // give the cached blocks back and retry
+        cudaGetLastError();
+        dev_trim(ctx);
+        e = cudaMalloc(out, want);
+    }
+    if (e == cudaSuccess) ctx->pool_size[*out] = want;
+    else *out = nullptr;
+    return e;
+}
+
+void dev_free(ss_ctx *ctx, void *ptr) {
+    if (!ptr) return;
+    auto it = ctx->pool_size.find(ptr);
+    if (it == ctx->pool_size.end()) { cudaFree(ptr); return; }
+    ctx->pool_free.emplace(it->second, ptr);
+}
+
+void dev_trim(ss_ctx *ctx) {
+    cudaDeviceSynchronize();
+    for (auto &kv : ctx->pool_free) { cudaFree(kv.second); ctx->pool_size.erase(kv.second); }
+    ctx->pool_free.clear();
+}
+
 ss_status cached_table(ss_ctx *ctx, std::tuple<int, int, int> key, size_t n_elems,
                        void (*fill)(Fp *dst, size_t n, int log_n, int variant), Fp **out) {
     auto it = ctx->tables.find(key);
@@ -67,6 +99,8 @@ void ss_destroy(ss_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    dev_trim(ctx);
+    for (auto &kv : ctx->pool_size) cudaFree(kv.first);       // blocks still held by live trees die with the context
     for (auto &kv : ctx->tables) cudaFree(kv.second);
     if (ctx->scratch) cudaFree(ctx->scratch);
     cudaStreamDestroy(ctx->stream);

@@ -22,6 +22,9 @@ struct ss_ctx {
     int sm_count = 148;
     unsigned long long launches = 0;          // kernels launched by this ctx (ss_kernel_launches)
     std::map<std::string, long long> options; // tuning switches / read-back values (ss_set_option, ss_get_option)
+    // device blocks released by dev_free, kept for reuse (size -> pointers) and the size of every live block
+    std::multimap<size_t, void *> pool_free;
+    std::map<void *, size_t> pool_size;
 };
 
 namespace ss {
@@ -53,6 +56,12 @@ inline ss_status fail(ss_ctx *ctx, ss_status code, const char *fmt, ...) {
 inline cudaStream_t pick_stream(ss_ctx *, void *stream) { return reinterpret_cast<cudaStream_t>(stream); }
 
 ss_status scratch_reserve(ss_ctx *ctx, size_t bytes, void **out);
+// Caching device allocator for the per-call work buffers (Merkle trees, OOD weights, partial sums): a prove step
+// asks for the same sizes again and again, and cudaMalloc / cudaFree of multi-GB blocks cost tens to hundreds of
+// milliseconds and synchronise the device.  Blocks are handed out again in stream order (one stream per ctx).
+cudaError_t dev_alloc(ss_ctx *ctx, void **out, size_t bytes);
+void dev_free(ss_ctx *ctx, void *ptr);
+void dev_trim(ss_ctx *ctx);
 // uploads a host table once and caches it; `fill` computes n elements of 32 bytes
 ss_status cached_table(ss_ctx *ctx, std::tuple<int, int, int> key, size_t n_elems,
                        void (*fill)(Fp *dst, size_t n, int log_n, int variant), Fp **out);

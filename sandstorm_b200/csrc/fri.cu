@@ -436,12 +436,12 @@ ss_status ss_ood_eval(ss_ctx *ctx, ss_field field, const void *d_trace_cols, uin
     Fp *d_w = nullptr, *d_part = nullptr, *d_out = nullptr;
     OodTap *d_taps = nullptr;
     int2 *d_where = nullptr;
-    cudaError_t ce = cudaMalloc(&d_w, row_count * sizeof(Fp));
-    if (ce == cudaSuccess) ce = cudaMalloc(&d_part, taps.size() * (size_t)n_chunks * 2 * sizeof(Fp));
-    if (ce == cudaSuccess) ce = cudaMalloc(&d_out, n_evals * sizeof(Fp));
-    if (ce == cudaSuccess) ce = cudaMalloc(&d_taps, taps.size() * sizeof(OodTap));
-    if (ce == cudaSuccess) ce = cudaMalloc(&d_where, n_evals * sizeof(int2));
-    auto cleanup = [&] { cudaFree(d_w); cudaFree(d_part); cudaFree(d_out); cudaFree(d_taps); cudaFree(d_where); };
+    cudaError_t ce = dev_alloc(ctx, reinterpret_cast<void **>(&d_w), row_count * sizeof(Fp));
+    if (ce == cudaSuccess) ce = dev_alloc(ctx, reinterpret_cast<void **>(&d_part), taps.size() * (size_t)n_chunks * 2 * sizeof(Fp));
+    if (ce == cudaSuccess) ce = dev_alloc(ctx, reinterpret_cast<void **>(&d_out), n_evals * sizeof(Fp));
+    if (ce == cudaSuccess) ce = dev_alloc(ctx, reinterpret_cast<void **>(&d_taps), taps.size() * sizeof(OodTap));
+    if (ce == cudaSuccess) ce = dev_alloc(ctx, reinterpret_cast<void **>(&d_where), n_evals * sizeof(int2));
+    auto cleanup = [&] { dev_free(ctx, d_w); dev_free(ctx, d_part); dev_free(ctx, d_out); dev_free(ctx, d_taps); dev_free(ctx, d_where); };
     if (ce != cudaSuccess) { cleanup(); return fail(ctx, SS_ERR_OOM, "ss_ood_eval: %s", cudaGetErrorString(ce)); }
     cudaMemcpy(d_taps, taps.data(), taps.size() * sizeof(OodTap), cudaMemcpyHostToDevice);
     cudaMemcpy(d_where, where.data(), n_evals * sizeof(int2), cudaMemcpyHostToDevice);
@@ -486,12 +486,12 @@ ss_status ss_poly_eval(ss_ctx *ctx, ss_field field, const void *d_coeffs, uint64
     const unsigned long long part0 = (n + 2047) / 2048;
     Fp *d_mult = nullptr, *d_a = nullptr, *d_b = nullptr;
     EvalJob *d_jobs = nullptr;
-    cudaError_t ce = cudaMalloc(&d_mult, mults.size() * sizeof(Fp));
-    if (ce == cudaSuccess) ce = cudaMalloc(&d_a, n_evals * part0 * sizeof(Fp));
-    if (ce == cudaSuccess) ce = cudaMalloc(&d_b, n_evals * ((part0 + 2047) / 2048) * sizeof(Fp));
-    if (ce == cudaSuccess) ce = cudaMalloc(&d_jobs, n_evals * sizeof(EvalJob));
+    cudaError_t ce = dev_alloc(ctx, reinterpret_cast<void **>(&d_mult), mults.size() * sizeof(Fp));
+    if (ce == cudaSuccess) ce = dev_alloc(ctx, reinterpret_cast<void **>(&d_a), n_evals * part0 * sizeof(Fp));
+    if (ce == cudaSuccess) ce = dev_alloc(ctx, reinterpret_cast<void **>(&d_b), n_evals * ((part0 + 2047) / 2048) * sizeof(Fp));
+    if (ce == cudaSuccess) ce = dev_alloc(ctx, reinterpret_cast<void **>(&d_jobs), n_evals * sizeof(EvalJob));
     if (ce != cudaSuccess) {
-        cudaFree(d_mult); cudaFree(d_a); cudaFree(d_b); cudaFree(d_jobs);
+        dev_free(ctx, d_mult); dev_free(ctx, d_a); dev_free(ctx, d_b); dev_free(ctx, d_jobs);
         return fail(ctx, SS_ERR_OOM, "ss_poly_eval: %s", cudaGetErrorString(ce));
     }
     cudaMemcpy(d_mult, mults.data(), mults.size() * sizeof(Fp), cudaMemcpyHostToDevice);
@@ -523,7 +523,7 @@ ss_status ss_poly_eval(ss_ctx *ctx, ss_field field, const void *d_coeffs, uint64
     // n_in == 1 per job now (blocks of the last stage == 1)
     std::vector<Fp> res(n_evals);
     ce = cudaMemcpy(res.data(), final_src, n_evals * sizeof(Fp), cudaMemcpyDeviceToHost);
-    cudaFree(d_mult); cudaFree(d_a); cudaFree(d_b); cudaFree(d_jobs);
+    dev_free(ctx, d_mult); dev_free(ctx, d_a); dev_free(ctx, d_b); dev_free(ctx, d_jobs);
     if (ce != cudaSuccess) return fail(ctx, SS_ERR_CUDA, "ss_poly_eval: %s", cudaGetErrorString(ce));
     memcpy(h_out, res.data(), n_evals * sizeof(Fp));
     return SS_OK;

@@ -275,9 +275,9 @@ ss_status ss_merkle_build(ss_ctx *ctx, ss_tree_kind kind, int n_friendly, const 
         if (rc) return rc;
     }
     ss_tree *t = new ss_tree{ctx, (int)kind, n_friendly, log_rows, n_cols, nullptr, nullptr};
-    cudaError_t e1 = cudaMalloc(&t->d_leaves, n * 32), e2 = cudaMalloc(&t->d_nodes, n * 32);
+    cudaError_t e1 = dev_alloc(ctx, reinterpret_cast<void **>(&t->d_leaves), n * 32), e2 = dev_alloc(ctx, reinterpret_cast<void **>(&t->d_nodes), n * 32);
     if (e1 != cudaSuccess || e2 != cudaSuccess) {
-        cudaFree(t->d_leaves); cudaFree(t->d_nodes); delete t;
+        dev_free(ctx, t->d_leaves); dev_free(ctx, t->d_nodes); delete t;
         cudaGetLastError();
         return fail(ctx, SS_ERR_OOM, "ss_merkle_build: cannot allocate %llu bytes for the tree", n * 64ull);
     }
@@ -340,7 +340,7 @@ ss_status ss_merkle_build(ss_ctx *ctx, ss_tree_kind kind, int n_friendly, const 
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
-        cudaFree(t->d_leaves); cudaFree(t->d_nodes); delete t;
+        dev_free(ctx, t->d_leaves); dev_free(ctx, t->d_nodes); delete t;
         return fail(ctx, SS_ERR_CUDA, "ss_merkle_build: launch failed: %s", cudaGetErrorString(e));
     }
     (void)rc;
@@ -453,8 +453,8 @@ int ss_tree_log_rows(const ss_tree *tree) { return tree ? tree->log_rows : -1; }
 void ss_tree_free(ss_tree *tree) {
     if (!tree) return;
     cudaSetDevice(tree->ctx->device);
-    cudaFree(tree->d_leaves);
-    cudaFree(tree->d_nodes);
+    dev_free(tree->ctx, tree->d_leaves);
+    dev_free(tree->ctx, tree->d_nodes);
     delete tree;
 }
 

@@ -133,8 +133,10 @@ class HotPathProver:
         dist.all_gather_into_tensor(full, full[lo:lo + cnt].clone())
 
     # ---- the device stages ---------------------------------------------------------------------------------
-    def prove(self, base: Matrix, ext: Matrix, queries: bool = True, self_check: bool = False) -> HotPathResult:
+    def prove(self, base: Matrix, ext: Matrix, queries: bool = True, self_check: bool = False, column_ready=None) -> HotPathResult:
         """base / ext: the trace columns (every rank holds them: they come from the host-side trace builder).
+        column_ready(k): optional hook called before trace column k (base then extension; None = all) is first read, so that a
+        caller streaming the trace from host memory can order its uploads against the LDE (bench.py e2e leg).
         With world > 1 (torch.distributed initialised, one process per GPU): LDE and OOD are sharded by column,
         Merkle hashing / constraint evaluation / DEEP / FRI folds by LDE row range; LDE columns are broadcast
         from their owners, row-sharded vectors all-gathered, sub-tree roots combined (SURVEY.md §8e plan A)."""
@@ -156,6 +158,8 @@ class HotPathProver:
 
         def lde_cols(src: Matrix, first_col: int):
             for j in owned_columns(src.num_cols, rank, world):
+                if column_ready is not None:
+                    column_ready(first_col + j)          # e.g. make the stream wait for the upload of this column
                 c.check(c.lib.ss_lde(c.handle, _lib.FIELD_FP252, ctypes.c_void_p(src.data[j].data_ptr()), n, 1, self.log_n, b,
                                      ctypes.c_void_p(lde[first_col + j].data_ptr()), N, None, n,
                                      _lib.ORDER_NATURAL, None))
@@ -178,6 +182,7 @@ class HotPathProver:
         prog = self.composition_program()
         inv_x_minus_c(all_lde[self.w_col], _mont(1), c)
         comp_evals = torch.empty((N, 4), dtype=torch.int64, device=dev)
+        self.mark("inv_w")
         evaluate(prog, Matrix(all_lde, c), b, out=comp_evals, rows=(row_lo, row_cnt) if world > 1 else None)
         self._gather_rows(comp_evals, row_lo, row_cnt)
         self.mark("constraint_eval")
@@ -198,6 +203,8 @@ class HotPathProver:
         #     weight vector, ss_ood_eval).  Each rank sums over its range of trace rows; the partial values add up.
         z = self._draw()
         taps = L.taps()
+        if column_ready is not None:
+            column_ready(None)                           # every trace column is read from here on
         t_lo, t_cnt = rank * (n // world), n // world
         parts = np.zeros((len(taps), 4), dtype=np.uint64)
         for mat, first, count in ((base, 0, nb), (ext, nb, C - nb)):
@@ -237,6 +244,7 @@ class HotPathProver:
         # (coset iNTT of size n, zero padding, coset NTT of size N).  Same polynomial, hence the same N evaluations.
         deep = torch.empty((N, 4), dtype=torch.int64, device=dev)
         sub_lo, sub_cnt = row_lo >> b, row_cnt >> b
+        self.mark("deep_setup")
         evaluate(deep_prog, Matrix(all_lde, c), b, out=deep[:n], rows=(row_lo, sub_cnt) if world > 1 else None, log_row_step=b)
         self._gather_rows(deep[:n], sub_lo, sub_cnt)
         self.mark("deep")
