@@ -66,3 +66,18 @@ def deep_expr_shifted(trace_terms, comp_terms, u_col: int, v_col: int, g: int, p
         q = (comp - Constant(comp_y)) * Trace(v_col, 0)
         total = q if total is None else total + q
     return total
+
+
+def deep_terms(taps, ood_trace, ood_composition, first_comp_col: int, alpha: int, p: int):
+    """Stark::gen_deep_coeffs (reference src/lib.rs:102-116): powers of one alpha, first over the trace arguments
+    (the taps, in air.trace_arguments() order) then over the composition columns.  Returns (trace_terms, comp_terms)
+    for deep_expr_shifted.  Note alpha^0 = 1: the first term has a unit coefficient, which is part of the program's
+    structure (tools/gen_ce_kernels.py builds its terms with this function for that reason)."""
+    t_terms, c_terms, k = [], [], 0
+    for (col, off), y in zip(taps, ood_trace):
+        t_terms.append((col, off, y, pow(alpha, k, p)))
+        k += 1
+    for j, y in enumerate(ood_composition):
+        c_terms.append((first_comp_col + j, y, pow(alpha, k, p)))
+        k += 1
+    return t_terms, c_terms

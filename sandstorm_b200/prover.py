@@ -26,7 +26,7 @@ import torch
 
 from . import _lib
 from .air import compile_program
-from .air.deep import deep_expr_shifted
+from .air.deep import deep_expr_shifted, deep_terms
 from .air.evaluate import evaluate
 from .air.expr import P
 from .air.layouts import load_layout
@@ -230,11 +230,7 @@ class HotPathProver:
         res.ood_trace, res.ood_composition = [v * rinv % P for v in ood_m], [v * rinv % P for v in to_int(ood_c)]
         # 12: DEEP composition over the LDE coset (coefficients = powers of one alpha, src/lib.rs:102-116)
         alpha = self._draw()
-        t_terms, c_terms, k = [], [], 0
-        for (col, off), y in zip(taps, res.ood_trace):
-            t_terms.append((col, off, y, pow(alpha, k, P))); k += 1
-        for j, y in enumerate(res.ood_composition):
-            c_terms.append((self.comp_col + j, y, pow(alpha, k, P))); k += 1
+        t_terms, c_terms = deep_terms(taps, res.ood_trace, res.ood_composition, self.comp_col, alpha, P)
         inv_x_minus_c(all_lde[self.u_col], _mont(z), c)
         inv_x_minus_c(all_lde[self.v_col], _mont(zc), c)
         deep_prog = compile_program(deep_expr_shifted(t_terms, c_terms, self.u_col, self.v_col, self.g, P), self.log_n, b)

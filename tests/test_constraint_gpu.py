@@ -202,7 +202,7 @@ def test_specialised_kernels_match_interpreter(ss, oracle, name, log_n):
     import torch
 
     from sandstorm_b200.air import compile_program
-    from sandstorm_b200.air.deep import deep_expr_shifted
+    from sandstorm_b200.air.deep import deep_expr_shifted, deep_terms
     from sandstorm_b200.air.evaluate import evaluate
     from sandstorm_b200.air.layouts import load_layout
 
@@ -218,8 +218,7 @@ def test_specialised_kernels_match_interpreter(ss, oracle, name, log_n):
     comp = compile_program(L.composition(n, inv_x_minus_one_col=C + ce), log_n, 1, [rnd.randrange(P) for _ in range(L.n_challenges())],
                            [rnd.randrange(P) for _ in range(L.n_hints())], [rnd.randrange(P)])
     g = pow(3, (P - 1) // n, P)
-    tt = [(col, off, rnd.randrange(P), rnd.randrange(P)) for col, off in L.taps()]
-    ct = [(C + j, rnd.randrange(P), rnd.randrange(P)) for j in range(ce)]
+    tt, ct = deep_terms(L.taps(), [rnd.randrange(P) for _ in L.taps()], [rnd.randrange(P) for _ in range(ce)], C, rnd.randrange(P), P)
     deep = compile_program(deep_expr_shifted(tt, ct, C + ce + 1, C + ce + 2, g, P), log_n, 1)
     try:
         for prog in (comp, deep):

@@ -13,7 +13,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import sandstorm_b200 as ss  # noqa: E402
 from sandstorm_b200.air import compile_program  # noqa: E402
-from sandstorm_b200.air.deep import deep_expr_shifted  # noqa: E402
+from sandstorm_b200.air.deep import deep_expr_shifted, deep_terms  # noqa: E402
 from sandstorm_b200.air.evaluate import evaluate  # noqa: E402
 from sandstorm_b200.air.expr import P  # noqa: E402
 from sandstorm_b200.air.layouts import load_layout  # noqa: E402
@@ -30,8 +30,7 @@ def main():
     comp = compile_program(L.composition(n, inv_x_minus_one_col=C + 2), log_n, log_b, [rnd.randrange(P) for _ in range(L.n_challenges())],
                            [rnd.randrange(P) for _ in range(L.n_hints())], [rnd.randrange(P)])
     g = pow(3, (P - 1) // n, P)
-    tt = [(c, off, rnd.randrange(P), rnd.randrange(P)) for c, off in L.taps()]
-    ct = [(C + j, rnd.randrange(P), rnd.randrange(P)) for j in range(2)]
+    tt, ct = deep_terms(L.taps(), [rnd.randrange(P) for _ in L.taps()], [rnd.randrange(P) for _ in range(2)], C, rnd.randrange(P), P)
     deep = compile_program(deep_expr_shifted(tt, ct, C + 3, C + 4, g, P), log_n, log_b)
     t_compile = time.time() - t0
     torch.cuda.set_device(0)

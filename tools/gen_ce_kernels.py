@@ -25,7 +25,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from sandstorm_b200.air import compile_program  # noqa: E402
-from sandstorm_b200.air.deep import deep_expr_shifted  # noqa: E402
+from sandstorm_b200.air.deep import deep_expr_shifted, deep_terms  # noqa: E402
 from sandstorm_b200.air.expr import P  # noqa: E402
 from sandstorm_b200.air.layouts import load_layout  # noqa: E402
 from sandstorm_b200.air.program import structure_hash  # noqa: E402
@@ -115,8 +115,7 @@ def programs():
                                [rnd.randrange(P) for _ in range(L.n_hints())], [rnd.randrange(P)], with_tables=False)
         out.append((f"{layout}_composition", comp.blob, 3))
         g = pow(3, (P - 1) // n, P)
-        tt = [(c, off, rnd.randrange(P), rnd.randrange(P)) for c, off in L.taps()]
-        ct = [(C + j, rnd.randrange(P), rnd.randrange(P)) for j in range(ce)]
+        tt, ct = deep_terms(L.taps(), [rnd.randrange(P) for _ in L.taps()], [rnd.randrange(P) for _ in range(ce)], C, rnd.randrange(P), P)
         deep = compile_program(deep_expr_shifted(tt, ct, C + ce + 1, C + ce + 2, g, P), log_n, 1, with_tables=False)
         out.append((f"{layout}_deep", deep.blob, 4))
     return out
