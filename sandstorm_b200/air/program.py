@@ -264,6 +264,18 @@ DOT_SLOT_CHUNK = 8                   # slot operands alive at once inside one DO
 DOT_MAX_TERMS = 4096
 
 
+SMALL_COEFF = 16                     # |c| <= this: c * A is a short chain of additions, not a multiplication
+
+
+def _small(c: int) -> int:
+    """signed value of a coefficient when it is a small integer (2 <= |s| <= SMALL_COEFF), else 0."""
+    if 2 <= c <= SMALL_COEFF:
+        return c
+    if 2 <= P - c <= SMALL_COEFF:
+        return c - P
+    return 0
+
+
 def _mul_bound(ba: int, bb: int) -> int:
     """exclusive upper bound of fp::mul / acc_reduce for operands below ba, bb (fp252.cuh: result <= a*b/R + p)."""
     return ba * bb // R + P + 1
@@ -358,7 +370,7 @@ def compile_program(expr: Expr, log_n: int, log_blowup: int, challenges=(), hint
         if c == 1:
             return a
         terms, c0 = a
-        if c == P - 1 or len(terms) <= 1 or all(v not in (1, P - 1) for v in terms.values()):
+        if c == P - 1 or len(terms) <= 1 or all(v not in (1, P - 1) and not _small(v) for v in terms.values()):
             return {k: v * c % P for k, v in terms.items()}, c0 * c % P
         return {node_of(a): c}, 0
 
@@ -562,10 +574,10 @@ def compile_program(expr: Expr, log_n: int, log_blowup: int, challenges=(), hint
 
     class Opnd:
         """an instruction operand: a leaf fetched in place, or a slot (owned by a node or temporary)."""
-        __slots__ = ("word", "slot", "nid")
+        __slots__ = ("word", "slot", "nid", "keep")
 
-        def __init__(self, word, slot=None, nid=None):
-            self.word, self.slot, self.nid = word, slot, nid
+        def __init__(self, word, slot=None, nid=None, keep=False):
+            self.word, self.slot, self.nid, self.keep = word, slot, nid, keep      # keep: an alias, released by its owner
 
         @property
         def b(self) -> int:
@@ -594,6 +606,8 @@ def compile_program(expr: Expr, log_n: int, log_blowup: int, challenges=(), hint
         return Opnd(K_SLOT << 29 | slot_of[nid], slot_of[nid], nid)
 
     def release(op: Opnd):
+        if op.keep:
+            return
         if op.nid is None:                                      # temporary
             if op.slot is not None:
                 free.append(op.slot)
@@ -686,12 +700,31 @@ def compile_program(expr: Expr, log_n: int, log_blowup: int, challenges=(), hint
         stats["dot"] += 1
         return Opnd(K_SLOT << 29 | d, d, None)
 
+    def multiple(op: Opnd, m: int) -> Opnd:
+        """m * op for a small integer m >= 2 by left-to-right double-and-add on raw additions; releases op."""
+        alias = lambda o: Opnd(o.word, o.slot, o.nid, keep=True)
+        cur = None
+        for bit in bin(m)[3:]:
+            src = cur if cur is not None else op
+            nxt = do_add(alias(src), alias(src))
+            if cur is not None:
+                release(cur)
+            cur = nxt
+            if bit == "1":
+                nxt = do_add(alias(cur), alias(op))
+                release(cur)
+                cur = nxt
+            stats["small"] = stats.get("small", 0) + 1
+        release(op)
+        return cur
+
     def const_opnd(v: int) -> Opnd:
         return Opnd(K_CONST << 29 | const_id(v))
 
     def emit_lc(nid: int):
         terms, c0 = g.args[nid]
-        gen = [(t, c) for t, c in terms if c not in (1, P - 1)]
+        small = [(t, _small(c)) for t, c in terms if _small(c)]
+        gen = [(t, c) for t, c in terms if c not in (1, P - 1) and not _small(c)]
         plus = [t for t, c in terms if c == 1]
         minus = [t for t, c in terms if c == P - 1]
         gen.sort(key=lambda tc: g.kind[resolve(tc[0])] in LEAF_KINDS)     # slot operands first, leaves fill the chunks up
@@ -721,6 +754,12 @@ def compile_program(expr: Expr, log_n: int, log_blowup: int, challenges=(), hint
         for t in minus:
             op = operand(t)
             acc = do_sub(acc if acc is not None else const_opnd(0), op)
+        for t, sm in small:
+            m = multiple(operand(t), abs(sm))
+            if sm > 0:
+                acc = m if acc is None else do_add(acc, m)
+            else:
+                acc = do_sub(acc if acc is not None else const_opnd(0), m)
         adopt(acc, nid)
 
     def emit(nid: int):
