@@ -124,15 +124,51 @@ __global__ void __launch_bounds__(256) poly_fold_kernel(const EvalJob *jobs, uns
 // Every denominator X - c * g^e of the AIR boundary terms and of the DEEP quotients is a shifted read of
 // this one vector:  x_i - c g^e = g^e (x_{i - b e} - c)  (g = w_N^b generates the trace domain).
 constexpr int INV_ROWS = 16;
-__global__ void __launch_bounds__(128) inv_x_minus_c_kernel(Fp *out, int log_n, Fp c, const Fp *xlo, const Fp *xhi) {
+constexpr int INV_THREADS = 128;
+
+// Inverse of every thread's value with ONE field inversion per block (Montgomery's trick as a product tree in
+// shared memory): up-sweep of pairwise products, thread 0 inverts the root (a^(p-2): 250 squarings + 11
+// multiplications — the other warps wait at the barrier and the SM runs other blocks), down-sweep
+// inv(left) = inv(node) * right, inv(right) = inv(node) * left.  sm: 2 * INV_THREADS elements.
+__device__ __forceinline__ Fp block_inverse(const Fp &v, Fp *sm) {
+    const int tid = threadIdx.x;
+    sm[INV_THREADS + tid] = v;
+    __syncthreads();
+    for (int w = INV_THREADS / 2; w >= 1; w >>= 1) {
+        if (tid < w) sm[w + tid] = fp::mul(sm[2 * (w + tid)], sm[2 * (w + tid) + 1]);
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const Fp acc = sm[1];
+        auto sqn = [](Fp x, int m) { for (int t = 0; t < m; ++t) x = fp::sqr(x); return x; };
+        const Fp e2 = fp::mul(sqn(acc, 1), acc), e4 = fp::mul(sqn(e2, 2), e2), e8 = fp::mul(sqn(e4, 4), e4);
+        const Fp e16 = fp::mul(sqn(e8, 8), e8), e32 = fp::mul(sqn(e16, 16), e16), e64 = fp::mul(sqn(e32, 32), e32);
+        const Fp e128 = fp::mul(sqn(e64, 64), e64), e192 = fp::mul(sqn(e128, 64), e64);
+        const Fp gq = fp::mul(e192, acc);
+        sm[1] = fp::mul(sqn(fp::mul(sqn(gq, 55), gq), 4), e192);
+    }
+    __syncthreads();
+    for (int w = 1; w < INV_THREADS; w <<= 1) {
+        if (tid < w) {
+            const int k = w + tid;
+            const Fp ik = sm[k], l = sm[2 * k], r = sm[2 * k + 1];
+            sm[2 * k] = fp::mul(ik, r);
+            sm[2 * k + 1] = fp::mul(ik, l);
+        }
+        __syncthreads();
+    }
+    return sm[INV_THREADS + tid];
+}
+__global__ void __launch_bounds__(INV_THREADS) inv_x_minus_c_kernel(Fp *out, int log_n, int log_step, Fp c, const Fp *xlo, const Fp *xhi) {
+    __shared__ Fp sm[2 * INV_THREADS];
     const unsigned long long n = 1ull << log_n;
     const unsigned long long chunk = (unsigned long long)blockDim.x * INV_ROWS;
-    const unsigned long long base = blockIdx.x * chunk + threadIdx.x;     // rows base + k * blockDim.x: coalesced stores
+    const unsigned long long base = blockIdx.x * chunk + threadIdx.x;     // rows (base + k * blockDim.x) << log_step
     Fp d[INV_ROWS], pre[INV_ROWS];
     Fp acc = fp::one();
 #pragma unroll
     for (int k = 0; k < INV_ROWS; ++k) {
-        const unsigned long long i = base + (unsigned long long)k * blockDim.x;
+        const unsigned long long i = (base + (unsigned long long)k * blockDim.x) << log_step;
         Fp x = fp::one();
         if (i < n) {
             x = ld_fp(xlo + (i & 4095ull));
@@ -143,16 +179,10 @@ __global__ void __launch_bounds__(128) inv_x_minus_c_kernel(Fp *out, int log_n, 
         pre[k] = acc;
         acc = fp::mul(acc, x);
     }
-    // inverse of the running product: a^(p-2), p - 2 = (2^59 + 2^4) * 2^192 + (2^192 - 1)
-    auto sqn = [](Fp v, int m) { for (int t = 0; t < m; ++t) v = fp::sqr(v); return v; };
-    const Fp e2 = fp::mul(sqn(acc, 1), acc), e4 = fp::mul(sqn(e2, 2), e2), e8 = fp::mul(sqn(e4, 4), e4);
-    const Fp e16 = fp::mul(sqn(e8, 8), e8), e32 = fp::mul(sqn(e16, 16), e16), e64 = fp::mul(sqn(e32, 32), e32);
-    const Fp e128 = fp::mul(sqn(e64, 64), e64), e192 = fp::mul(sqn(e128, 64), e64);
-    const Fp gq = fp::mul(e192, acc);
-    Fp inv = fp::mul(sqn(fp::mul(sqn(gq, 55), gq), 4), e192);
+    Fp inv = block_inverse(acc, sm);
 #pragma unroll
     for (int k = INV_ROWS - 1; k >= 0; --k) {
-        const unsigned long long i = base + (unsigned long long)k * blockDim.x;
+        const unsigned long long i = (base + (unsigned long long)k * blockDim.x) << log_step;
         const Fp t = fp::mul(inv, pre[k]);
         inv = fp::mul(inv, d[k]);
         if (i < n) st_fp(out + i, fp::canon(t));
@@ -168,8 +198,9 @@ __global__ void __launch_bounds__(128) inv_x_minus_c_kernel(Fp *out, int log_n, 
 // splits over row ranges (one per GPU).
 //
 // bary_weights_kernel: W_j for j in [row_begin, row_begin + count), Montgomery batch inversion per thread.
-__global__ void __launch_bounds__(128) bary_weights_kernel(Fp *out, unsigned long long row_begin, unsigned long long count, Fp z,
-                                                             const Fp *ginv_lo, const Fp *ginv_hi) {
+__global__ void __launch_bounds__(INV_THREADS) bary_weights_kernel(Fp *out, unsigned long long row_begin, unsigned long long count, Fp z,
+                                                                     const Fp *ginv_lo, const Fp *ginv_hi) {
+    __shared__ Fp sm[2 * INV_THREADS];
     const unsigned long long chunk = (unsigned long long)blockDim.x * INV_ROWS;
     const unsigned long long base = blockIdx.x * chunk + threadIdx.x;
     Fp d[INV_ROWS], pre[INV_ROWS];
@@ -188,12 +219,7 @@ __global__ void __launch_bounds__(128) bary_weights_kernel(Fp *out, unsigned lon
         pre[k] = acc;
         acc = fp::mul(acc, x);
     }
-    auto sqn = [](Fp v, int m) { for (int t = 0; t < m; ++t) v = fp::sqr(v); return v; };
-    const Fp e2 = fp::mul(sqn(acc, 1), acc), e4 = fp::mul(sqn(e2, 2), e2), e8 = fp::mul(sqn(e4, 4), e4);
-    const Fp e16 = fp::mul(sqn(e8, 8), e8), e32 = fp::mul(sqn(e16, 16), e16), e64 = fp::mul(sqn(e32, 32), e32);
-    const Fp e128 = fp::mul(sqn(e64, 64), e64), e192 = fp::mul(sqn(e128, 64), e64);
-    const Fp gq = fp::mul(e192, acc);
-    Fp inv = fp::mul(sqn(fp::mul(sqn(gq, 55), gq), 4), e192);
+    Fp inv = block_inverse(acc, sm);
 #pragma unroll
     for (int k = INV_ROWS - 1; k >= 0; --k) {
         const unsigned long long t = base + (unsigned long long)k * blockDim.x;
@@ -364,10 +390,10 @@ ss_status ss_fri_fold(ss_ctx *ctx, ss_field field, const void *d_evals, int log_
     return SS_OK;
 }
 
-ss_status ss_inv_x_minus_c(ss_ctx *ctx, ss_field field, int log_n, const void *h_c, void *d_out, void *stream) {
+ss_status ss_inv_x_minus_c(ss_ctx *ctx, ss_field field, int log_n, int log_row_step, const void *h_c, void *d_out, void *stream) {
     if (!ctx) return SS_ERR_INVALID;
     if (field != SS_FIELD_FP252) return fail(ctx, SS_ERR_UNSUPPORTED, "ss_inv_x_minus_c: field %d not built", (int)field);
-    if (!h_c || !d_out || log_n < 0 || log_n > 40) return fail(ctx, SS_ERR_INVALID, "ss_inv_x_minus_c: bad arguments");
+    if (!h_c || !d_out || log_n < 0 || log_n > 40 || log_row_step < 0 || log_row_step > log_n) return fail(ctx, SS_ERR_INVALID, "ss_inv_x_minus_c: bad arguments");
     SS_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
     const size_t n = (size_t)1 << log_n;
     Fp *lo, *hi;
@@ -375,8 +401,10 @@ ss_status ss_inv_x_minus_c(ss_ctx *ctx, ss_field field, int log_n, const void *h
     // x_i = 3 * w_N^i: same tables (and cache keys) as the constraint evaluator's OP_X
     if ((rc = cached_table(ctx, {20, log_n, 0}, n < 4096 ? n : 4096, [](Fp *d, size_t m, int ln, int) { fill_x_lo(d, m, ln, 3); }, &lo))) return rc;
     if ((rc = cached_table(ctx, {21, log_n, 0}, n <= 4096 ? 1 : n / 4096, fill_x_hi, &hi))) return rc;
-    const unsigned long long chunk = 128ull * INV_ROWS;
-    inv_x_minus_c_kernel<<<(unsigned)((n + chunk - 1) / chunk), 128, 0, pick_stream(ctx, stream)>>>(static_cast<Fp *>(d_out), log_n, fp::canon(load_host(h_c)), lo, hi);
+    const unsigned long long chunk = (unsigned long long)INV_THREADS * INV_ROWS;
+    const size_t rows = n >> log_row_step;
+    inv_x_minus_c_kernel<<<(unsigned)((rows + chunk - 1) / chunk), INV_THREADS, 0, pick_stream(ctx, stream)>>>(static_cast<Fp *>(d_out), log_n, log_row_step,
+                                                                                                            fp::canon(load_host(h_c)), lo, hi);
     ctx->launches++;
     SS_CUDA_CHECK(ctx, cudaGetLastError());
     return SS_OK;
@@ -445,8 +473,8 @@ ss_status ss_ood_eval(ss_ctx *ctx, ss_field field, const void *d_trace_cols, uin
     if (ce != cudaSuccess) { cleanup(); return fail(ctx, SS_ERR_OOM, "ss_ood_eval: %s", cudaGetErrorString(ce)); }
     cudaMemcpy(d_taps, taps.data(), taps.size() * sizeof(OodTap), cudaMemcpyHostToDevice);
     cudaMemcpy(d_where, where.data(), n_evals * sizeof(int2), cudaMemcpyHostToDevice);
-    const unsigned long long wchunk = 128ull * INV_ROWS;
-    bary_weights_kernel<<<(unsigned)((row_count + wchunk - 1) / wchunk), 128>>>(d_w, row_begin, row_count, z, lo, hi);
+    const unsigned long long wchunk = (unsigned long long)INV_THREADS * INV_ROWS;
+    bary_weights_kernel<<<(unsigned)((row_count + wchunk - 1) / wchunk), INV_THREADS>>>(d_w, row_begin, row_count, z, lo, hi);
     if ((unsigned long long)taps.size() * n_chunks > 0x7fffffffull) { cleanup(); return fail(ctx, SS_ERR_UNSUPPORTED, "ss_ood_eval: grid too large"); }
     ood_dot_kernel<<<(unsigned)(taps.size() * n_chunks), OOD_THREADS>>>(static_cast<const Fp *>(d_trace_cols), col_stride, log_n, d_w, row_begin,
                                                                            row_count, d_taps, (unsigned)taps.size(), n_chunks, d_part);

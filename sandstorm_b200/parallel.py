@@ -3,7 +3,9 @@ GPU, torch.distributed for the exchange.  The functions are backend-agnostic (NC
 CPU test-suite): they only decide who owns what and move whole columns / 32-byte sub-roots.
 
     LDE      : column j is transformed by rank j % world            (no communication)
-    exchange : every LDE column is broadcast from its owner          (NCCL over NVLink)
+    exchange : every rank receives, from the owner of each column, the rows it will consume: its own row range
+               plus a halo of max_offset * blowup rows for the constraint taps (share_row_ranges; point-to-point
+               sends grouped into one NCCL launch — 1/world of the traffic of broadcasting whole columns)
     Merkle   : rank r hashes rows [r*N/world, (r+1)*N/world) and builds that sub-tree;
                the world sub-roots are all-gathered (32 B each) and combined (ss_merkle_combine)
 """
@@ -34,6 +36,43 @@ def share_columns(matrix: torch.Tensor, world: int) -> None:
         return
     for j in range(matrix.shape[0]):
         dist.broadcast(matrix[j], src=owner_of(j, world))
+
+
+def share_row_ranges(matrix: torch.Tensor, world: int, rank: int, halo: int) -> None:
+    """In place: after the call rank r holds, for EVERY column, the rows [r*step, (r+1)*step + halo) (mod N) — what the
+    row-sharded consumers read (Merkle leaves, constraint evaluation with its forward taps, DEEP).  Column j is
+    complete on its owner before the call.  matrix: [n_cols, N, limbs]."""
+    if world == 1:
+        return
+    n_cols, N = matrix.shape[0], matrix.shape[1]
+    step = N // world
+    if halo > step:                                   # tiny domains: the halo would span several ranks
+        share_columns(matrix, world)
+        return
+    ops = []
+    for j in range(n_cols):
+        o = owner_of(j, world)
+        for r in range(world):
+            if r == o:
+                continue
+            rows = matrix[j, r * step:(r + 1) * step]
+            if rank == o:
+                ops.append(dist.P2POp(dist.isend, rows, r))
+            elif rank == r:
+                ops.append(dist.P2POp(dist.irecv, rows, o))
+    for req in (dist.batch_isend_irecv(ops) if ops else []):
+        req.wait()
+    if halo == 0:
+        return
+    # halo: the `halo` rows after my range are the first rows of the next rank's range (wrapping at N)
+    nxt, prv = (rank + 1) % world, (rank - 1) % world
+    lo = ((rank + 1) * step) % N
+    ops = []
+    for j in range(n_cols):
+        ops.append(dist.P2POp(dist.isend, matrix[j, rank * step:rank * step + halo], prv))
+        ops.append(dist.P2POp(dist.irecv, matrix[j, lo:lo + halo], nxt))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
 
 
 def gather_subroots(my_root: bytes, world: int, device) -> list[bytes]:

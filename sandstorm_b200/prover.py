@@ -142,7 +142,7 @@ class HotPathProver:
         from their owners, row-sharded vectors all-gathered, sub-tree roots combined (SURVEY.md §8e plan A)."""
         opt, L = self.opt, self.layout
         assert base.num_cols == L.num_base_columns and ext.num_cols == L.num_extension_columns and base.num_rows == self.n
-        from .parallel import owned_columns, share_columns
+        from .parallel import owned_columns, share_row_ranges
 
         res = HotPathResult()
         dev, world, rank = self.device, self.world, self.rank
@@ -167,14 +167,15 @@ class HotPathProver:
         # 3-5: base trace
         lde_cols(base, 0)
         self.mark("lde_base")
-        share_columns(lde[:nb], world)
+        halo = L.max_offset << b                      # forward reach of the constraint taps, in LDE rows
+        share_row_ranges(lde[:nb], world, rank, halo)
         self.mark("share_base")
         res.roots["base"], h = self._commit(lde.data_ptr(), N, nb, self.log_n + b); handles.append(h)
         self.mark("merkle_base")
         # 8: extension trace
         lde_cols(ext, nb)
         self.mark("lde_ext")
-        share_columns(lde[nb:], world)
+        share_row_ranges(lde[nb:], world, rank, halo)
         self.mark("share_ext")
         res.roots["ext"], h = self._commit(lde[nb].data_ptr(), N, C - nb, self.log_n + b); handles.append(h)
         self.mark("merkle_ext")
@@ -195,7 +196,12 @@ class HotPathProver:
         comp_lde.zero_()
         comp_lde[:, :n] = comp_coeffs
         self.mark("comp_split")
-        Matrix(comp_lde, c).ntt_(coset=True)
+        if world == 1:
+            Matrix(comp_lde, c).ntt_(coset=True)
+        else:                                            # one composition column per rank, then the row ranges
+            for j in owned_columns(self.ce, rank, world):
+                Matrix(comp_lde[j:j + 1], c).ntt_(coset=True)
+            share_row_ranges(comp_lde, world, rank, 0)
         self.mark("ntt_comp_fwd")
         res.roots["composition"], h = self._commit(comp_lde.data_ptr(), N, self.ce, self.log_n + b); handles.append(h)
         self.mark("merkle_comp")
@@ -231,8 +237,9 @@ class HotPathProver:
         # 12: DEEP composition over the LDE coset (coefficients = powers of one alpha, src/lib.rs:102-116)
         alpha = self._draw()
         t_terms, c_terms = deep_terms(taps, res.ood_trace, res.ood_composition, self.comp_col, alpha, P)
-        inv_x_minus_c(all_lde[self.u_col], _mont(z), c)
-        inv_x_minus_c(all_lde[self.v_col], _mont(zc), c)
+        # (the sub-coset evaluation below reads u and v only at rows that are multiples of the blowup)
+        inv_x_minus_c(all_lde[self.u_col], _mont(z), c, log_row_step=b)
+        inv_x_minus_c(all_lde[self.v_col], _mont(zc), c, log_row_step=b)
         deep_prog = compile_program(deep_expr_shifted(t_terms, c_terms, self.u_col, self.v_col, self.g, P), self.log_n, b)
         del comp_coeffs, comp_evals, work
         # The quotient has degree < n - 1, so its n values on the sub-coset 3<w_n> — the LDE rows that are multiples of
@@ -250,6 +257,8 @@ class HotPathProver:
         self.mark("deep_lde")
         if self_check and world == 1:
             # test hook: the extended quotient equals the row-by-row evaluation on the whole LDE coset
+            inv_x_minus_c(all_lde[self.u_col], _mont(z), c)
+            inv_x_minus_c(all_lde[self.v_col], _mont(zc), c)
             res.deep_matches_full_evaluation = bool(torch.equal(deep, evaluate(deep_prog, Matrix(all_lde, c), b)))
         # 13: FRI layers
         evals, log_size, offset = deep, self.log_n + b, 3

@@ -32,8 +32,14 @@ def _worker(rank, world, port, cols_np, q):
         lde = torch.zeros((n_cols, N, 4), dtype=torch.int64)
         for j in parallel.owned_columns(n_cols, rank, world):
             lde[j] = torch.from_numpy(oracle.lde(cols_np[j:j + 1], 1)[0].view(np.int64))
-        parallel.share_columns(lde, world)
+        # row-range exchange (what the prover uses): my rows + a halo of 5 rows of every column, nothing else needed
+        part = lde.clone()
+        parallel.share_row_ranges(part, world, rank, halo=5)
         lo, hi = parallel.row_range(N, rank, world)
+        need = [(lo + k) % N for k in range(hi - lo + 5)]
+        want_full = torch.from_numpy(oracle.lde(cols_np, 1).view(np.int64))
+        assert torch.equal(part[:, need], want_full[:, need]), "row-range exchange"
+        parallel.share_columns(lde, world)
         sub = np.ascontiguousarray(lde[:, lo:hi].numpy().view(np.uint64))
         my_root = oracle.merkle_build(oracle.TREE_KECCAK_M20, sub)[2]
         roots = parallel.gather_subroots(my_root, world, "cpu")
