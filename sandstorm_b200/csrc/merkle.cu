@@ -348,6 +348,18 @@ ss_status ss_merkle_build(ss_ctx *ctx, ss_tree_kind kind, int n_friendly, const 
     return SS_OK;
 }
 
+// PedersenDigest::as_bytes: big-endian canonical integer (crypto/src/hash/pedersen.rs:23-28) of a stored felt
+static void felt_to_be_bytes(const uint8_t raw[32], uint8_t out[32]) {
+    Fp m, one_int = fp::zero();
+    one_int.l[0] = 1;
+    for (int i = 0; i < 8; ++i) m.l[i] = (uint32_t)raw[4 * i] | ((uint32_t)raw[4 * i + 1] << 8) | ((uint32_t)raw[4 * i + 2] << 16) | ((uint32_t)raw[4 * i + 3] << 24);
+    const Fp c = fp::canon(fp::mul(m, one_int));
+    for (int w = 0; w < 8; ++w) {
+        const uint32_t v = c.l[7 - w];
+        out[4 * w] = (uint8_t)(v >> 24); out[4 * w + 1] = (uint8_t)(v >> 16); out[4 * w + 2] = (uint8_t)(v >> 8); out[4 * w + 3] = (uint8_t)v;
+    }
+}
+
 ss_status ss_merkle_root(ss_ctx *ctx, const ss_tree *tree, uint8_t root[32]) {
     if (!ctx || !tree || !root) return SS_ERR_INVALID;
     uint8_t raw[32];
@@ -358,15 +370,7 @@ ss_status ss_merkle_root(ss_ctx *ctx, const ss_tree *tree, uint8_t root[32]) {
         for (int i = 0; i < 32; ++i) root[i] = raw[i];
         return SS_OK;
     }
-    // PedersenDigest::as_bytes: big-endian canonical integer (crypto/src/hash/pedersen.rs:23-28)
-    Fp m, one_int = fp::zero();
-    one_int.l[0] = 1;
-    for (int i = 0; i < 8; ++i) m.l[i] = (uint32_t)raw[4 * i] | ((uint32_t)raw[4 * i + 1] << 8) | ((uint32_t)raw[4 * i + 2] << 16) | ((uint32_t)raw[4 * i + 3] << 24);
-    const Fp c = fp::canon(fp::mul(m, one_int));
-    for (int w = 0; w < 8; ++w) {
-        const uint32_t v = c.l[7 - w];
-        root[4 * w] = (uint8_t)(v >> 24); root[4 * w + 1] = (uint8_t)(v >> 16); root[4 * w + 2] = (uint8_t)(v >> 8); root[4 * w + 3] = (uint8_t)v;
-    }
+    felt_to_be_bytes(raw, root);
     return SS_OK;
 }
 
@@ -426,25 +430,40 @@ ss_status ss_merkle_open(ss_ctx *ctx, const ss_tree *tree, const uint64_t *h_ind
 // root of the tree whose leaves they are.  Used when each GPU commits a row range.
 ss_status ss_merkle_combine(ss_ctx *ctx, ss_tree_kind kind, const uint8_t *h_subroots, int log_count, uint8_t root[32]) {
     if (!ctx || !h_subroots || !root || log_count < 0 || log_count > 16) return SS_ERR_INVALID;
-    if (kind == SS_TREE_FRIENDLY) return fail(ctx, SS_ERR_UNSUPPORTED, "ss_merkle_combine: algebraic top layers are not sharded");
     const unsigned long long count = 1ull << log_count;
     if (log_count == 0) { for (int i = 0; i < 32; ++i) root[i] = h_subroots[i]; return SS_OK; }
     int bh, mask;
     byte_hash_of(kind, bh, mask);
+    PedersenTable tab{nullptr};
+    if (kind == SS_TREE_FRIENDLY) {
+        // The top log_count levels of a friendly tree are algebraic as long as log_count <= N_FRIENDLY (22): the
+        // sub-roots arrive as ss_merkle_root returns them (big-endian bytes: a masked digest or a canonical felt,
+        // both below p), so the first level is hash_boundary + Pedersen and the rest plain Pedersen merges.
+        ss_status rc = pedersen_table(ctx, &tab);
+        if (rc) return rc;
+    }
     uint8_t *d = nullptr;                       // nodes[count .. 2count) = sub-roots, nodes[1] = root
-    SS_CUDA_CHECK(ctx, cudaMalloc(&d, 2 * count * 32));
+    SS_CUDA_CHECK(ctx, dev_alloc(ctx, reinterpret_cast<void **>(&d), 2 * count * 32));
     cudaMemcpy(d + 32 * count, h_subroots, count * 32, cudaMemcpyHostToDevice);
     for (int lvl = log_count - 1; lvl >= 0; --lvl) {
         const unsigned long long c = 1ull << lvl;
-        by_byte_hash(bh, [&](auto BH) {
-            node_hash_kernel<decltype(BH)::value><<<grid_for(c, 128), 128>>>(d + 64ull * c, c, mask, d + 32ull * c);
+        if (kind == SS_TREE_FRIENDLY) {
+            pedersen_node_kernel<<<grid_for(c, 128), 128>>>(d + 64ull * c, c, lvl == log_count - 1 ? 1 : 0, tab, d + 32ull * c);
             ctx->launches++;
-            return SS_OK;
-        });
+        } else {
+            by_byte_hash(bh, [&](auto BH) {
+                node_hash_kernel<decltype(BH)::value><<<grid_for(c, 128), 128>>>(d + 64ull * c, c, mask, d + 32ull * c);
+                ctx->launches++;
+                return SS_OK;
+            });
+        }
     }
-    cudaError_t e = cudaMemcpy(root, d + 32, 32, cudaMemcpyDeviceToHost);
-    cudaFree(d);
+    uint8_t raw[32];
+    cudaError_t e = cudaMemcpy(raw, d + 32, 32, cudaMemcpyDeviceToHost);
+    dev_free(ctx, d);
     if (e != cudaSuccess) return fail(ctx, SS_ERR_CUDA, "ss_merkle_combine: %s", cudaGetErrorString(e));
+    if (kind == SS_TREE_FRIENDLY) felt_to_be_bytes(raw, root);
+    else for (int i = 0; i < 32; ++i) root[i] = raw[i];
     return SS_OK;
 }
 

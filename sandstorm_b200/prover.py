@@ -47,7 +47,8 @@ class ProofOptions:
     log_blowup: int = 1
     log_fold: int = 3
     max_remainder_coeffs: int = 16
-    tree_kind: int = _lib.TREE_KECCAK_M20
+    tree_kind: int = _lib.TREE_KECCAK_M20        # src/claims.rs:18-21 (starknet / EthVerifier); recursive claims use TREE_FRIENDLY
+    n_friendly: int = 22                         # NUM_FRIENDLY_COMMITMENT_LAYERS, src/claims.rs:10 (TREE_FRIENDLY only)
 
 
 @dataclass
@@ -112,7 +113,11 @@ class HotPathProver:
         rows = 1 << log_rows
         lo, cnt = (rank * (rows // world), rows // world) if shard else (0, rows)
         handle = ctypes.c_void_p()
-        c.check(c.lib.ss_merkle_build(c.handle, opt.tree_kind, 0, ctypes.c_void_p(ptr + 32 * lo), col_stride, n_cols,
+        # Pedersen levels are counted from the root of the WHOLE tree: a sub-tree below log2(world) levels keeps the rest
+        friendly = 0
+        if opt.tree_kind == _lib.TREE_FRIENDLY:
+            friendly = max(0, opt.n_friendly - (world.bit_length() - 1)) if shard else opt.n_friendly
+        c.check(c.lib.ss_merkle_build(c.handle, opt.tree_kind, friendly, ctypes.c_void_p(ptr + 32 * lo), col_stride, n_cols,
                                       cnt.bit_length() - 1, _lib.ORDER_NATURAL, ctypes.byref(handle), None))
         root = (ctypes.c_uint8 * 32)()
         c.check(c.lib.ss_merkle_root(c.handle, handle, root))

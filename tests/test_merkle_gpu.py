@@ -133,3 +133,27 @@ def test_large_tree_root_of_roots(ss, oracle):
             assert t.root() == oracle.merkle_build(oracle.TREE_KECCAK_M20, sub)[2]
     H = lambda x, y: oracle.hash_bytes(oracle.HASH_KECCAK_M20, x + y)
     assert tree.root() == H(H(quarter_roots[0], quarter_roots[1]), H(quarter_roots[2], quarter_roots[3]))
+
+
+@pytest.mark.parametrize("name,n_friendly,n_cols,log_rows", [("keccak_m20", 0, 9, 8), ("friendly", 3, 3, 6), ("friendly", 2, 7, 7), ("friendly", 22, 2, 5)])
+def test_sharded_commit_combines_to_the_whole_tree(ss, oracle, name, n_friendly, n_cols, log_rows):
+    """The multi-GPU commitment: 4 row-range sub-trees (Pedersen levels counted from the root of the WHOLE tree, so a
+    sub-tree keeps n_friendly - 2 of them) + ss_merkle_combine over the 4 sub-roots == the root of the whole tree."""
+    import ctypes
+
+    from sandstorm_b200.merkle import MatrixMerkleTree
+
+    gk, ok = kind_ids(ss, oracle, name)
+    rng = np.random.default_rng(3000 + log_rows)
+    cols = oracle.random_felts(rng, n_cols, 1 << log_rows)
+    want = oracle.merkle_build(ok, cols, n_friendly=n_friendly)[2]
+    quarter = 1 << (log_rows - 2)
+    subs = b""
+    for q in range(4):
+        sub = np.ascontiguousarray(cols[:, q * quarter:(q + 1) * quarter])
+        subs += MatrixMerkleTree.from_matrix(ss.Matrix.from_numpy(sub), gk, n_friendly=max(0, n_friendly - 2)).root()
+    c = ss.default_context()
+    root = (ctypes.c_uint8 * 32)()
+    buf = (ctypes.c_uint8 * 128).from_buffer_copy(subs)
+    c.check(c.lib.ss_merkle_combine(c.handle, gk, buf, 2, root))
+    assert bytes(root) == want

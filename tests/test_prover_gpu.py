@@ -18,14 +18,16 @@ def ss():
     return sandstorm_b200
 
 
-@pytest.mark.parametrize("layout,log_n", [("plain", 7), ("recursive", 12)])
-def test_hot_path_is_consistent(ss, oracle, layout, log_n):
+@pytest.mark.parametrize("layout,log_n,tree", [("plain", 7, "keccak_m20"), ("recursive", 12, "keccak_m20"), ("recursive", 11, "friendly")])
+def test_hot_path_is_consistent(ss, oracle, layout, log_n, tree):
     import torch
 
     from sandstorm_b200.prover import HotPathProver, ProofOptions
 
     P = oracle.P
-    hp = HotPathProver(layout, log_n, ProofOptions(num_queries=12))
+    # recursive claims commit with FriendlyMerkleTree<22, Blake2s masked / Pedersen> (src/claims.rs:10,29-32)
+    gk, ok = (ss.TREE_FRIENDLY, oracle.TREE_FRIENDLY) if tree == "friendly" else (ss.TREE_KECCAK_M20, oracle.TREE_KECCAK_M20)
+    hp = HotPathProver(layout, log_n, ProofOptions(num_queries=12, tree_kind=gk))
     L = hp.layout
     rng = np.random.default_rng(log_n)
     base = oracle.random_felts(rng, L.num_base_columns, 1 << log_n)
@@ -35,8 +37,8 @@ def test_hot_path_is_consistent(ss, oracle, layout, log_n):
     # the DEEP quotient, evaluated on the sub-coset 3<w_n> and extended, equals its evaluation on every LDE row
     assert res.deep_matches_full_evaluation is True
     # commitments
-    assert res.roots["base"] == oracle.merkle_build(oracle.TREE_KECCAK_M20, oracle.lde(base, 1))[2]
-    assert res.roots["ext"] == oracle.merkle_build(oracle.TREE_KECCAK_M20, oracle.lde(ext, 1))[2]
+    assert res.roots["base"] == oracle.merkle_build(ok, oracle.lde(base, 1))[2]
+    assert res.roots["ext"] == oracle.merkle_build(ok, oracle.lde(ext, 1))[2]
     # out-of-domain values of two taps
     coeffs = oracle.ntt(np.concatenate([base, ext]), inverse=True)
     taps = L.taps()
