@@ -172,3 +172,24 @@ def merkle_build(kind: int, cols: np.ndarray, n_friendly: int = 22, bitrev_rows:
     root = ctypes.create_string_buffer(32)
     lib().oracle_merkle_root_bytes(ctypes.c_int(kind), ctypes.c_int(n_friendly), ctypes.c_int(n_cols), ctypes.c_int(log_rows), _ptr(nodes), root)
     return nodes, leaves, root.raw
+
+
+# ----------------------------------------------------------------- Goldilocks (p = 2^64 - 2^32 + 1), stored words x * 2^64 mod p
+GL_P = 2**64 - 2**32 + 1
+GL_GENERATOR = 7
+
+
+def gl_ntt(cols: np.ndarray, inverse: bool = False, coset: bool = False) -> np.ndarray:
+    """cols: uint64[n_cols, n] stored words.  Natural order in and out (ark-poly fft / ifft / coset forms)."""
+    a = np.ascontiguousarray(cols, dtype=np.uint64).copy()
+    n_cols, n = a.shape
+    lib().oracle_gl_ntt_cols(_ptr(a), ctypes.c_size_t(n_cols), ctypes.c_int(n.bit_length() - 1), ctypes.c_int(int(inverse)), ctypes.c_int(int(coset)))
+    return a
+
+
+def gl_lde(cols: np.ndarray, log_blowup: int) -> np.ndarray:
+    a = np.ascontiguousarray(cols, dtype=np.uint64)
+    n_cols, n = a.shape
+    out = np.empty((n_cols, n << log_blowup), dtype=np.uint64)
+    lib().oracle_gl_lde_cols(_ptr(a), ctypes.c_size_t(n_cols), ctypes.c_int(n.bit_length() - 1), ctypes.c_int(log_blowup), _ptr(out))
+    return out

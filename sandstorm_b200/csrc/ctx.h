@@ -62,6 +62,11 @@ ss_status scratch_reserve(ss_ctx *ctx, size_t bytes, void **out);
 cudaError_t dev_alloc(ss_ctx *ctx, void **out, size_t bytes);
 void dev_free(ss_ctx *ctx, void *ptr);
 void dev_trim(ss_ctx *ctx);
+// Goldilocks transforms (ntt_goldilocks.cu): one u64 per element, same semantics as the Fp252 entry points
+ss_status gl_ntt(ss_ctx *ctx, void *d_cols, uint64_t col_stride, int n_cols, int log_n, int inverse, int coset, ss_order in_order,
+                 ss_order out_order, cudaStream_t st);
+ss_status gl_lde(ss_ctx *ctx, const void *d_trace, uint64_t trace_stride, int n_cols, int log_n, int log_blowup, void *d_lde,
+                 uint64_t lde_stride, void *d_coeffs, uint64_t coeff_stride, ss_order out_order, cudaStream_t st);
 // uploads a host table once and caches it; `fill` computes n elements of 32 bytes
 ss_status cached_table(ss_ctx *ctx, std::tuple<int, int, int> key, size_t n_elems,
                        void (*fill)(Fp *dst, size_t n, int log_n, int variant), Fp **out);

@@ -132,3 +132,13 @@ void hc_f28_sub(const uint32_t *a, const uint32_t *b, int dit, uint32_t *out) {
     F28 r = dit ? f28::sub_dit(x, y) : f28::sub_dif(x, y); std::memcpy(out, r.l, 36);
 }
 }
+
+// ---- Goldilocks single-limb arithmetic (goldilocks.cuh) ----
+#include "goldilocks.cuh"
+extern "C" {
+uint64_t hc_gl_add(uint64_t a, uint64_t b) { return gl::add(a, b); }
+uint64_t hc_gl_sub(uint64_t a, uint64_t b) { return gl::sub(a, b); }
+uint64_t hc_gl_mul(uint64_t a, uint64_t b) { return gl::mul(a, b); }
+uint64_t hc_gl_reduce128(uint64_t lo, uint64_t hi) { return gl::reduce128(lo, hi); }
+uint64_t hc_gl_root(int log_n) { return gl::root_of_unity(log_n); }
+}

@@ -258,12 +258,16 @@ extern "C" {
 ss_status ss_ntt(ss_ctx *ctx, ss_field field, void *d_cols, uint64_t col_stride, int n_cols, int log_n,
                  int inverse, int coset, ss_order in_order, ss_order out_order, void *stream) {
     if (!ctx) return SS_ERR_INVALID;
-    if (field != SS_FIELD_FP252) return fail(ctx, SS_ERR_UNSUPPORTED, "ss_ntt: field %d not built", (int)field);
+    if (field != SS_FIELD_FP252 && field != SS_FIELD_GOLDILOCKS) return fail(ctx, SS_ERR_UNSUPPORTED, "ss_ntt: field %d not built", (int)field);
     if (!d_cols || n_cols < 0 || log_n < 0 || log_n > 40 || col_stride < (1ull << log_n))
         return fail(ctx, SS_ERR_INVALID, "ss_ntt: bad arguments (n_cols=%d log_n=%d stride=%llu)", n_cols, log_n, (unsigned long long)col_stride);
     if (n_cols == 0) return SS_OK;
     SS_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = pick_stream(ctx, stream);
+    if (field == SS_FIELD_GOLDILOCKS) {
+        if (log_n > 32) return fail(ctx, SS_ERR_INVALID, "ss_ntt: Goldilocks has 2-adicity 32");
+        return gl_ntt(ctx, d_cols, col_stride, n_cols, log_n, inverse, coset, in_order, out_order, st);
+    }
     NttJob job{};
     job.dst = static_cast<Fp *>(d_cols);
     job.src = job.dst;
@@ -291,7 +295,7 @@ ss_status ss_lde(ss_ctx *ctx, ss_field field, const void *d_trace, uint64_t trac
                  int log_n, int log_blowup, void *d_lde, uint64_t lde_stride, void *d_coeffs,
                  uint64_t coeff_stride, ss_order out_order, void *stream) {
     if (!ctx) return SS_ERR_INVALID;
-    if (field != SS_FIELD_FP252) return fail(ctx, SS_ERR_UNSUPPORTED, "ss_lde: field %d not built", (int)field);
+    if (field != SS_FIELD_FP252 && field != SS_FIELD_GOLDILOCKS) return fail(ctx, SS_ERR_UNSUPPORTED, "ss_lde: field %d not built", (int)field);
     if (!d_trace || !d_lde || n_cols < 0 || log_n < 0 || log_blowup < 0 || log_n + log_blowup > 40 ||
         trace_stride < (1ull << log_n) || lde_stride < (1ull << (log_n + log_blowup)) ||
         (d_coeffs && coeff_stride < (1ull << log_n)))
@@ -299,6 +303,10 @@ ss_status ss_lde(ss_ctx *ctx, ss_field field, const void *d_trace, uint64_t trac
     if (n_cols == 0) return SS_OK;
     SS_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = pick_stream(ctx, stream);
+    if (field == SS_FIELD_GOLDILOCKS) {
+        if (log_n + log_blowup > 32) return fail(ctx, SS_ERR_INVALID, "ss_lde: Goldilocks has 2-adicity 32");
+        return gl_lde(ctx, d_trace, trace_stride, n_cols, log_n, log_blowup, d_lde, lde_stride, d_coeffs, coeff_stride, out_order, st);
+    }
     const size_t n = (size_t)1 << log_n;
     Fp *coeffs = static_cast<Fp *>(d_coeffs);
     uint64_t cstride = coeff_stride;
