@@ -43,6 +43,11 @@ LOG_BLOWUP = 1                              # cli/src/main.rs:53-54 (lde_blowup_
 CYCLE_HEIGHT_LOG = 4                        # n = 16 * n_steps (layouts/src/starknet/mod.rs)
 
 
+def workload_name(log_n: int) -> str:
+    return (f"starknet layout, 2^{log_n - CYCLE_HEIGHT_LOG} Cairo steps (n=2^{log_n} rows, LDE 2^{log_n + LOG_BLOWUP}), Fp252, "
+            f"{N_BASE}+{N_EXT} trace + {N_COMP} composition columns, masked-Keccak Merkle")
+
+
 def ntt_ops(log_len: int) -> float:
     return 1.5 * (1 << log_len) * log_len
 
@@ -153,7 +158,8 @@ def reference_arm(args):
         "impl": "reference", "metric": "ntt_field_ops_per_s", "value": value, "unit": "field-ops/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": info["lde_s_per_rep"] * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u256 (Fp252 Montgomery, 4 x u64)", "data": "synthetic",
-        "config": {"workload": f"starknet layout, 2^{args.log_steps} Cairo steps, Fp252, blowup 2 — bounded CPU sample of the LDE stage",
+        "config": {"workload": workload_name(args.log_steps + CYCLE_HEIGHT_LOG), "requested_log_steps": args.log_steps,
+                   "sample": "bounded CPU sample of the workload's LDE stage (2 columns of 2^18 rows per step), all host threads",
                    "note": "reference binary unavailable (Rust toolchain and ministark crates absent): restated CPU oracle, OpenMP"},
         "cpu_baseline": {"value": value, "unit": "field-ops/s", "cores": info["cores"], "kind": "port", "sample": info["sample"]},
         "e2e": {"value": value, "unit": "field-ops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -527,7 +533,7 @@ def gpu_arm(args):
         "metric": "ntt_field_ops_per_s", "value": value, "unit": "field-ops/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "prove_seconds": ms_per_step / 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u256 (Fp252 Montgomery, 8 x u32 limbs)", "data": "synthetic",
-        "config": {"workload": f"starknet layout, 2^{log_n - CYCLE_HEIGHT_LOG} Cairo steps (n=2^{log_n} rows, LDE 2^{log_n + LOG_BLOWUP}), Fp252, {N_BASE}+{N_EXT} trace + {N_COMP} composition columns, masked-Keccak Merkle",
+        "config": {"workload": workload_name(log_n),
                    "requested_log_steps": args.log_steps, "parallelism": f"{world} rank(s): LDE sharded by column (NCCL broadcast), Merkle + constraint eval + DEEP + FRI folds by LDE row range and OOD by trace row range (all-gather, combined sub-roots / summed partial values); composition-column and DEEP-extension NTTs replicated", "l2": "inputs_larger_than_L2",
                    "stages_in_step": list(stages.keys()),
                    "not_in_step": [] if isinstance(hp, FullHotPath) else ["constraint_eval (stand-in column)", "ood", "deep_composition", "fri_layers", "queries"],
