@@ -440,14 +440,22 @@ def gpu_arm(args):
     # ---- end-to-end through host buffers (pinned host trace -> H2D -> LDE -> commit -> D2H roots) ---
     e2e = None
     if not args.no_e2e:
-        h_base = torch.empty(hp.base.shape, dtype=torch.int64).pin_memory()
-        h_ext = torch.empty(hp.ext.shape, dtype=torch.int64).pin_memory()
-        h_base.copy_(hp.base); h_ext.copy_(hp.ext)
-        h2d = h_base.numel() * 8 + h_ext.numel() * 8
-
         copy_stream = torch.cuda.Stream()
-        n_trace_cols = hp.base.shape[0] + hp.ext.shape[0]
-
+        nb_cols = hp.base.shape[0]
+        n_trace_cols = nb_cols + hp.ext.shape[0]
+        dev_col = lambda k: hp.base[k] if k < nb_cols else hp.ext[k - nb_cols]
+        # what this rank has to upload: whole columns it transforms, and of the others only the rows it reads
+        owned, pieces = None, [(0, hp.n)]
+        if isinstance(hp, FullHotPath) and world > 1:
+            owned = set(hp.prover.trace_columns_owned())
+            lo, cnt = hp.prover.trace_rows_needed()
+            pieces = [(lo, min(hp.n, lo + cnt))] + ([(0, lo + cnt - hp.n)] if lo + cnt > hp.n else [])
+        # pinned host copy of exactly those rows, per column: [(device slice, pinned host tensor), ...]
+        plan = []
+        for k in range(n_trace_cols):
+            parts = [(0, hp.n)] if (owned is None or k in owned) else pieces
+            plan.append([(dev_col(k)[a:b], dev_col(k)[a:b].cpu().pin_memory()) for a, b in parts])
+        my_h2d = sum(h.numel() * 8 for col in plan for _, h in col)
         def e2e_step():
             # the trace is uploaded column by column on a copy stream; the LDE of column k waits only for column k,
             # so the rest of the H2D traffic overlaps the first LDE stage
@@ -456,8 +464,8 @@ def gpu_arm(args):
             events = []
             with torch.cuda.stream(copy_stream):
                 for k in range(n_trace_cols):
-                    dst, src = (hp.base[k], h_base[k]) if k < hp.base.shape[0] else (hp.ext[k - hp.base.shape[0]], h_ext[k - hp.base.shape[0]])
-                    dst.copy_(src, non_blocking=True)
+                    for dst, src in plan[k]:
+                        dst.copy_(src, non_blocking=True)
                     ev = torch.cuda.Event()
                     ev.record(copy_stream)
                     events.append(ev)
@@ -486,6 +494,10 @@ def gpu_arm(args):
         if world > 1:
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         e2e_ms = float(t[0])
+        hb = torch.tensor([float(my_h2d)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            torch.distributed.all_reduce(hb)
+        h2d = int(hb[0])                               # summed over the ranks
         d2h = 32 * 3
         if getattr(hp, "last", None) is not None:
             r = hp.last
@@ -493,7 +505,7 @@ def gpu_arm(args):
         e2e = {"value": hp.ntt_field_ops() / (e2e_ms * 1e-3), "unit": "field-ops/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
                "note": "whole committed-LDE call incl. copies, hashing and tree build in the denominator"}
-        del h_base, h_ext
+        del plan
 
     if rank != 0:
         return

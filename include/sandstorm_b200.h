@@ -147,6 +147,7 @@ ss_status ss_fri_fold(ss_ctx *ctx, ss_field field, const void *d_evals, int log_
  * g = w_N^b, every boundary denominator X - g^e of the AIR (c = 1) and every DEEP denominator
  * X - z g^e (c = z) is a shifted read of such a vector. */
 ss_status ss_inv_x_minus_c(ss_ctx *ctx, ss_field field, int log_n, int log_row_step /* only rows that are multiples of 2^step are written */,
+                           uint64_t row_begin, uint64_t row_count /* in units of 2^step rows, wrapping mod N; 0 = all */,
                            const void *h_c, void *d_out, void *stream);
 /* Out-of-domain evaluations (trace / composition polynomials at z * g^k): for e < n_evals,
  * h_out[e] = poly_{h_cols[e]}(h_points[e]).  natural_order = 0: the coefficient matrix ss_lde writes

@@ -839,3 +839,21 @@ def structure_hash(blob: bytes) -> int:
         for sh in (0, 8, 16, 24):
             h = ((h ^ ((v >> sh) & 0xFF)) * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
     return h
+
+
+def tap_reach(blob: bytes, log_rows: int) -> dict:
+    """{column: (most negative, most positive)} signed row offsets (in LDE rows) of the taps of a program blob — what a
+    rank that evaluates a row range has to hold of each column beyond the range itself (multi-GPU halos)."""
+    w = struct.unpack_from("<16I", blob, 0)
+    n_tables, n_taps = w[4], w[8]
+    nt = n_tables + (n_tables & 1)
+    taps = struct.unpack_from(f"<{2 * n_taps}I", blob, 64 + 8 * nt)
+    N = 1 << log_rows
+    out: dict = {}
+    for t in range(n_taps):
+        col, off = taps[2 * t], taps[2 * t + 1]
+        if off >= N // 2:
+            off -= N
+        lo, hi = out.get(col, (0, 0))
+        out[col] = (min(lo, off), max(hi, off))
+    return out

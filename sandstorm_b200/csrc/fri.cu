@@ -159,18 +159,20 @@ __device__ __forceinline__ Fp block_inverse(const Fp &v, Fp *sm) {
     }
     return sm[INV_THREADS + tid];
 }
-__global__ void __launch_bounds__(INV_THREADS) inv_x_minus_c_kernel(Fp *out, int log_n, int log_step, Fp c, const Fp *xlo, const Fp *xhi) {
+__global__ void __launch_bounds__(INV_THREADS) inv_x_minus_c_kernel(Fp *out, int log_n, int log_step, unsigned long long first, unsigned long long count, Fp c,
+                                                                      const Fp *xlo, const Fp *xhi) {
     __shared__ Fp sm[2 * INV_THREADS];
-    const unsigned long long n = 1ull << log_n;
+    const unsigned long long mask = (1ull << log_n) - 1;
     const unsigned long long chunk = (unsigned long long)blockDim.x * INV_ROWS;
-    const unsigned long long base = blockIdx.x * chunk + threadIdx.x;     // rows (base + k * blockDim.x) << log_step
+    const unsigned long long base = blockIdx.x * chunk + threadIdx.x;     // rows ((first + base + k * blockDim.x) << log_step) mod N
     Fp d[INV_ROWS], pre[INV_ROWS];
     Fp acc = fp::one();
 #pragma unroll
     for (int k = 0; k < INV_ROWS; ++k) {
-        const unsigned long long i = (base + (unsigned long long)k * blockDim.x) << log_step;
+        const unsigned long long t = base + (unsigned long long)k * blockDim.x;
+        const unsigned long long i = ((first + t) << log_step) & mask;
         Fp x = fp::one();
-        if (i < n) {
+        if (t < count) {
             x = ld_fp(xlo + (i & 4095ull));
             if (i >> 12) x = fp::mul(x, ld_fp(xhi + (i >> 12)));
             x = fp::sub(x, c);
@@ -182,10 +184,11 @@ __global__ void __launch_bounds__(INV_THREADS) inv_x_minus_c_kernel(Fp *out, int
     Fp inv = block_inverse(acc, sm);
 #pragma unroll
     for (int k = INV_ROWS - 1; k >= 0; --k) {
-        const unsigned long long i = (base + (unsigned long long)k * blockDim.x) << log_step;
-        const Fp t = fp::mul(inv, pre[k]);
+        const unsigned long long t = base + (unsigned long long)k * blockDim.x;
+        const unsigned long long i = ((first + t) << log_step) & mask;
+        const Fp r = fp::mul(inv, pre[k]);
         inv = fp::mul(inv, d[k]);
-        if (i < n) st_fp(out + i, fp::canon(t));
+        if (t < count) st_fp(out + i, fp::canon(r));
     }
 }
 
@@ -390,7 +393,8 @@ ss_status ss_fri_fold(ss_ctx *ctx, ss_field field, const void *d_evals, int log_
     return SS_OK;
 }
 
-ss_status ss_inv_x_minus_c(ss_ctx *ctx, ss_field field, int log_n, int log_row_step, const void *h_c, void *d_out, void *stream) {
+ss_status ss_inv_x_minus_c(ss_ctx *ctx, ss_field field, int log_n, int log_row_step, uint64_t row_begin, uint64_t row_count,
+                           const void *h_c, void *d_out, void *stream) {
     if (!ctx) return SS_ERR_INVALID;
     if (field != SS_FIELD_FP252) return fail(ctx, SS_ERR_UNSUPPORTED, "ss_inv_x_minus_c: field %d not built", (int)field);
     if (!h_c || !d_out || log_n < 0 || log_n > 40 || log_row_step < 0 || log_row_step > log_n) return fail(ctx, SS_ERR_INVALID, "ss_inv_x_minus_c: bad arguments");
@@ -402,9 +406,11 @@ ss_status ss_inv_x_minus_c(ss_ctx *ctx, ss_field field, int log_n, int log_row_s
     if ((rc = cached_table(ctx, {20, log_n, 0}, n < 4096 ? n : 4096, [](Fp *d, size_t m, int ln, int) { fill_x_lo(d, m, ln, 3); }, &lo))) return rc;
     if ((rc = cached_table(ctx, {21, log_n, 0}, n <= 4096 ? 1 : n / 4096, fill_x_hi, &hi))) return rc;
     const unsigned long long chunk = (unsigned long long)INV_THREADS * INV_ROWS;
-    const size_t rows = n >> log_row_step;
-    inv_x_minus_c_kernel<<<(unsigned)((rows + chunk - 1) / chunk), INV_THREADS, 0, pick_stream(ctx, stream)>>>(static_cast<Fp *>(d_out), log_n, log_row_step,
-                                                                                                            fp::canon(load_host(h_c)), lo, hi);
+    // rows (row_begin + t) << step, t < row_count, wrapping mod N (a rank's row range plus the halo its shifted reads need)
+    if (row_count == 0) { row_begin = 0; row_count = n >> log_row_step; }
+    if (row_count > (n >> log_row_step)) return fail(ctx, SS_ERR_INVALID, "ss_inv_x_minus_c: row range larger than the domain");
+    inv_x_minus_c_kernel<<<(unsigned)((row_count + chunk - 1) / chunk), INV_THREADS, 0, pick_stream(ctx, stream)>>>(
+        static_cast<Fp *>(d_out), log_n, log_row_step, row_begin, row_count, fp::canon(load_host(h_c)), lo, hi);
     ctx->launches++;
     SS_CUDA_CHECK(ctx, cudaGetLastError());
     return SS_OK;

@@ -19,7 +19,7 @@ ss_status ss_rows_gather(ss_ctx *ctx, const void *, uint64_t, int, const uint64_
 #endif
 
 #ifndef SS_HAVE_FRI
-ss_status ss_inv_x_minus_c(ss_ctx *ctx, ss_field, int, int, const void *, void *, void *) { return fail(ctx, SS_ERR_UNSUPPORTED, "ss_inv_x_minus_c: not built"); }
+ss_status ss_inv_x_minus_c(ss_ctx *ctx, ss_field, int, int, uint64_t, uint64_t, const void *, void *, void *) { return fail(ctx, SS_ERR_UNSUPPORTED, "ss_inv_x_minus_c: not built"); }
 ss_status ss_fri_fold(ss_ctx *ctx, ss_field, const void *, int, int, const void *, const void *, int, uint64_t, uint64_t, void *, void *) { return fail(ctx, SS_ERR_UNSUPPORTED, "ss_fri_fold: not built"); }
 ss_status ss_poly_eval(ss_ctx *ctx, ss_field, const void *, uint64_t, int, int, const int32_t *, const void *, size_t, void *) { return fail(ctx, SS_ERR_UNSUPPORTED, "ss_poly_eval: not built"); }
 ss_status ss_ood_eval(ss_ctx *ctx, ss_field, const void *, uint64_t, int, const int32_t *, const uint64_t *, size_t, const void *, uint64_t, uint64_t, void *) { return fail(ctx, SS_ERR_UNSUPPORTED, "ss_ood_eval: not built"); }

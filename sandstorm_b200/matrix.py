@@ -137,11 +137,15 @@ def ood_eval(trace: "Matrix", cols, offsets, z_mont: np.ndarray, rows: tuple[int
     return out
 
 
-def inv_x_minus_c(out: torch.Tensor, c_mont: np.ndarray, ctx: Context | None = None, log_row_step: int = 0) -> torch.Tensor:
+def inv_x_minus_c(out: torch.Tensor, c_mont: np.ndarray, ctx: Context | None = None, log_row_step: int = 0,
+                  rows: tuple[int, int] | None = None) -> torch.Tensor:
     """out[i] = 1 / (3 * w_N^i - c) for the N = out.shape[0] points of the LDE coset (ss_inv_x_minus_c); with
-    log_row_step only the rows that are multiples of 2^log_row_step are computed and written."""
+    log_row_step only the rows that are multiples of 2^log_row_step are computed and written; rows = (begin, count)
+    in units of 2^log_row_step rows (begin may be negative: the range wraps mod N) restricts the work to one
+    rank's row range plus the halo its shifted reads need."""
     ctx = ctx or default_context(out.device.index)
     n = out.shape[0]
-    ctx.check(ctx.lib.ss_inv_x_minus_c(ctx.handle, _lib.FIELD_FP252, n.bit_length() - 1, log_row_step, _felt_bytes(c_mont),
+    begin, count = rows if rows is not None else (0, 0)
+    ctx.check(ctx.lib.ss_inv_x_minus_c(ctx.handle, _lib.FIELD_FP252, n.bit_length() - 1, log_row_step, begin % (n >> log_row_step), count, _felt_bytes(c_mont),
                                        ctypes.c_void_p(out.data_ptr()), _stream_ptr()))
     return out

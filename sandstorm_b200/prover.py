@@ -26,6 +26,7 @@ import torch
 
 from . import _lib
 from .air import compile_program
+from .air.program import tap_reach
 from .air.deep import deep_expr_shifted, deep_terms
 from .air.evaluate import evaluate
 from .air.expr import P
@@ -82,6 +83,20 @@ class HotPathProver:
         self._composition_program = None
         self._challenges = self._hints = self._alpha = None
         self.timeline: list = []
+
+    # ---- what this rank reads of the trace (for callers that stream it from the host) -----------------------------
+    def trace_columns_owned(self) -> list[int]:
+        """trace columns (base then extension) whose LDE this rank computes: it needs them completely."""
+        from .parallel import owned_columns
+
+        nb, ne = self.layout.num_base_columns, self.layout.num_extension_columns
+        return owned_columns(nb, self.rank, self.world) + [nb + j for j in owned_columns(ne, self.rank, self.world)]
+
+    def trace_rows_needed(self) -> tuple[int, int]:
+        """(first row, count) of the trace rows this rank reads of EVERY column (the out-of-domain dot products over its
+        row range reach max_offset rows further; wraps mod n)."""
+        step = self.n // self.world
+        return self.rank * step, min(self.n, step + (self.layout.max_offset if self.world > 1 else 0))
 
     # ---- host-side stand-ins for the public coin -------------------------------------------------------
     def _draw(self) -> int:
@@ -186,7 +201,14 @@ class HotPathProver:
         self.mark("merkle_ext")
         # 9: constraint evaluation (row range of this rank), boundary denominators from w = 1/(x - 1)
         prog = self.composition_program()
-        inv_x_minus_c(all_lde[self.w_col], _mont(1), c)
+        if world == 1:
+            inv_x_minus_c(all_lde[self.w_col], _mont(1), c)
+        else:                                            # only the rows this rank's taps reach
+            lo_w, hi_w = tap_reach(prog.blob, self.log_n + b).get(self.w_col, (0, 0))
+            if hi_w - lo_w >= N // 4:                    # tiny domains: signed offsets are ambiguous, take every row
+                inv_x_minus_c(all_lde[self.w_col], _mont(1), c)
+            else:
+                inv_x_minus_c(all_lde[self.w_col], _mont(1), c, rows=(row_lo + lo_w, min(N, row_cnt + hi_w - lo_w)))
         comp_evals = torch.empty((N, 4), dtype=torch.int64, device=dev)
         self.mark("inv_w")
         evaluate(prog, Matrix(all_lde, c), b, out=comp_evals, rows=(row_lo, row_cnt) if world > 1 else None)
@@ -243,9 +265,18 @@ class HotPathProver:
         alpha = self._draw()
         t_terms, c_terms = deep_terms(taps, res.ood_trace, res.ood_composition, self.comp_col, alpha, P)
         # (the sub-coset evaluation below reads u and v only at rows that are multiples of the blowup)
-        inv_x_minus_c(all_lde[self.u_col], _mont(z), c, log_row_step=b)
-        inv_x_minus_c(all_lde[self.v_col], _mont(zc), c, log_row_step=b)
         deep_prog = compile_program(deep_expr_shifted(t_terms, c_terms, self.u_col, self.v_col, self.g, P), self.log_n, b)
+        if world == 1:
+            inv_x_minus_c(all_lde[self.u_col], _mont(z), c, log_row_step=b)
+            inv_x_minus_c(all_lde[self.v_col], _mont(zc), c, log_row_step=b)
+        else:
+            reach = tap_reach(deep_prog.blob, self.log_n + b)
+            for col, point in ((self.u_col, z), (self.v_col, zc)):
+                lo_t, hi_t = reach.get(col, (0, 0))
+                first, cnt = (row_lo + lo_t) >> b, min(n, (row_cnt + hi_t - lo_t + (1 << b) - 1) >> b)
+                if hi_t - lo_t >= N // 4:
+                    first, cnt = 0, n
+                inv_x_minus_c(all_lde[col], _mont(point), c, log_row_step=b, rows=(first, cnt))
         del comp_coeffs, comp_evals, work
         # The quotient has degree < n - 1, so its n values on the sub-coset 3<w_n> — the LDE rows that are multiples of
         # the blowup — determine it: evaluate only those (1/blowup of the work), then extend like any other column
