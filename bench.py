@@ -318,7 +318,9 @@ class FullHotPath(HotPath):
 
         self.base, self.ext = rand_cols(N_BASE, self.n), rand_cols(N_EXT, self.n)
         self.ctx = ss.default_context()
-        self.prover = HotPathProver("starknet", log_n, rank=rank, world=world)
+        from sandstorm_b200.prover import ProofOptions
+
+        self.prover = HotPathProver("starknet", log_n, ProofOptions(col_pad_rows=int(os.environ.get("SS_COL_PAD_ROWS", "0"))), rank=rank, world=world)
         t0 = time.perf_counter()
         self.program = self.prover.composition_program()        # host-side compile, outside every timed region
         self.compile_s = time.perf_counter() - t0

@@ -21,7 +21,7 @@ def evaluate(program: CompiledProgram, lde: Matrix, log_blowup: int, out: torch.
     if out is None:
         out = torch.empty((lde.num_rows >> log_row_step, 4), dtype=torch.int64, device=lde.data.device)
     begin, count = rows if rows is not None else (0, 0)
-    c.check(c.lib.ss_constraint_eval(c.handle, program.blob, len(program.blob), ctypes.c_void_p(lde.data.data_ptr()), lde.num_rows,
+    c.check(c.lib.ss_constraint_eval(c.handle, program.blob, len(program.blob), ctypes.c_void_p(lde.data.data_ptr()), lde.col_stride,
                                      lde.num_cols, lde.log_rows - log_blowup, log_blowup, begin, count, log_row_step,
                                      ctypes.c_void_p(out.data_ptr()), _stream_ptr()))
     return out

@@ -22,7 +22,8 @@ class Matrix:
     def __init__(self, data: torch.Tensor, ctx: Context | None = None):
         if data.dtype != torch.int64 or data.dim() != 3 or data.shape[2] != 4 or not data.is_cuda:
             raise ValueError("Matrix expects a CUDA int64 tensor of shape (n_cols, n_rows, 4)")
-        if not data.is_contiguous():
+        # columns may be padded: any column stride >= the number of rows is fine as long as each column is contiguous
+        if not (data.stride(2) == 1 and data.stride(1) == 4 and data.stride(0) % 4 == 0 and data.stride(0) >= 4 * data.shape[1]):
             data = data.contiguous()
         n = data.shape[1]
         if n & (n - 1):
@@ -48,6 +49,11 @@ class Matrix:
         return self.data.shape[1]
 
     @property
+    def col_stride(self) -> int:
+        """elements between consecutive columns (>= num_rows; the `col_stride` argument of the C ABI)."""
+        return self.data.stride(0) // 4 if self.data.shape[0] > 1 else max(self.num_rows, self.data.stride(0) // 4)
+
+    @property
     def log_rows(self) -> int:
         return self.num_rows.bit_length() - 1
 
@@ -58,7 +64,7 @@ class Matrix:
     def ntt_(self, inverse: bool = False, coset: bool = False, in_order: int = _lib.ORDER_NATURAL,
              out_order: int = _lib.ORDER_NATURAL) -> "Matrix":
         c = self.ctx
-        c.check(c.lib.ss_ntt(c.handle, _lib.FIELD_FP252, ctypes.c_void_p(self.data.data_ptr()), self.num_rows,
+        c.check(c.lib.ss_ntt(c.handle, _lib.FIELD_FP252, ctypes.c_void_p(self.data.data_ptr()), self.col_stride,
                              self.num_cols, self.log_rows, int(inverse), int(coset), in_order, out_order, _stream_ptr()))
         return self
 
@@ -115,7 +121,7 @@ def poly_eval(coeffs: "Matrix", cols, points_mont: np.ndarray, natural_order: bo
     pts = np.ascontiguousarray(points_mont, dtype=np.uint64).reshape(-1, 4)
     out = np.zeros_like(pts)
     torch.cuda.current_stream().synchronize()
-    ctx.check(ctx.lib.ss_poly_eval(ctx.handle, _lib.FIELD_FP252, ctypes.c_void_p(coeffs.data.data_ptr()), coeffs.num_rows, coeffs.log_rows,
+    ctx.check(ctx.lib.ss_poly_eval(ctx.handle, _lib.FIELD_FP252, ctypes.c_void_p(coeffs.data.data_ptr()), coeffs.col_stride, coeffs.log_rows,
                                    int(natural_order), cols.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), pts.ctypes.data_as(ctypes.c_void_p), len(cols),
                                    out.ctypes.data_as(ctypes.c_void_p)))
     return out
@@ -131,7 +137,7 @@ def ood_eval(trace: "Matrix", cols, offsets, z_mont: np.ndarray, rows: tuple[int
     out = np.zeros((len(cols), 4), dtype=np.uint64)
     begin, count = rows if rows is not None else (0, 0)
     torch.cuda.current_stream().synchronize()
-    ctx.check(ctx.lib.ss_ood_eval(ctx.handle, _lib.FIELD_FP252, ctypes.c_void_p(trace.data.data_ptr()), trace.num_rows, trace.log_rows,
+    ctx.check(ctx.lib.ss_ood_eval(ctx.handle, _lib.FIELD_FP252, ctypes.c_void_p(trace.data.data_ptr()), trace.col_stride, trace.log_rows,
                                   cols.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), offs.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), len(cols),
                                   _felt_bytes(z_mont), begin, count, out.ctypes.data_as(ctypes.c_void_p)))
     return out

@@ -50,6 +50,7 @@ class ProofOptions:
     max_remainder_coeffs: int = 16
     tree_kind: int = _lib.TREE_KECCAK_M20        # src/claims.rs:18-21 (starknet / EthVerifier); recursive claims use TREE_FRIENDLY
     n_friendly: int = 22                         # NUM_FRIENDLY_COMMITMENT_LAYERS, src/claims.rs:10 (TREE_FRIENDLY only)
+    col_pad_rows: int = 0                        # padding between the columns of the working matrix (not a protocol parameter)
 
 
 @dataclass
@@ -173,7 +174,8 @@ class HotPathProver:
         handles = []
         self.mark("start")
         # one matrix for every committed column: trace | composition (ce) | w | u | v  (see __init__)
-        all_lde = torch.empty((C + self.ce + 3, N, 4), dtype=torch.int64, device=dev)
+        S = N + opt.col_pad_rows                         # column stride of the working matrix
+        all_lde = torch.empty((C + self.ce + 3, S, 4), dtype=torch.int64, device=dev)[:, :N]
         lde = all_lde[:C]
 
         def lde_cols(src: Matrix, first_col: int):
@@ -181,7 +183,7 @@ class HotPathProver:
                 if column_ready is not None:
                     column_ready(first_col + j)          # e.g. make the stream wait for the upload of this column
                 c.check(c.lib.ss_lde(c.handle, _lib.FIELD_FP252, ctypes.c_void_p(src.data[j].data_ptr()), n, 1, self.log_n, b,
-                                     ctypes.c_void_p(lde[first_col + j].data_ptr()), N, None, n,
+                                     ctypes.c_void_p(lde[first_col + j].data_ptr()), S, None, n,
                                      _lib.ORDER_NATURAL, None))
 
         # 3-5: base trace
@@ -190,14 +192,14 @@ class HotPathProver:
         halo = L.max_offset << b                      # forward reach of the constraint taps, in LDE rows
         share_row_ranges(lde[:nb], world, rank, halo)
         self.mark("share_base")
-        res.roots["base"], h = self._commit(lde.data_ptr(), N, nb, self.log_n + b); handles.append(h)
+        res.roots["base"], h = self._commit(lde.data_ptr(), S, nb, self.log_n + b); handles.append(h)
         self.mark("merkle_base")
         # 8: extension trace
         lde_cols(ext, nb)
         self.mark("lde_ext")
         share_row_ranges(lde[nb:], world, rank, halo)
         self.mark("share_ext")
-        res.roots["ext"], h = self._commit(lde[nb].data_ptr(), N, C - nb, self.log_n + b); handles.append(h)
+        res.roots["ext"], h = self._commit(lde[nb].data_ptr(), S, C - nb, self.log_n + b); handles.append(h)
         self.mark("merkle_ext")
         # 9: constraint evaluation (row range of this rank), boundary denominators from w = 1/(x - 1)
         prog = self.composition_program()
@@ -230,7 +232,7 @@ class HotPathProver:
                 Matrix(comp_lde[j:j + 1], c).ntt_(coset=True)
             share_row_ranges(comp_lde, world, rank, 0)
         self.mark("ntt_comp_fwd")
-        res.roots["composition"], h = self._commit(comp_lde.data_ptr(), N, self.ce, self.log_n + b); handles.append(h)
+        res.roots["composition"], h = self._commit(comp_lde.data_ptr(), S, self.ce, self.log_n + b); handles.append(h)
         self.mark("merkle_comp")
         # 11: out-of-domain evaluations of every tap, straight from the trace (barycentric dot products with one shared
         #     weight vector, ss_ood_eval).  Each rank sums over its range of trace rows; the partial values add up.
@@ -325,7 +327,7 @@ class HotPathProver:
                 c.check(c.lib.ss_merkle_open(c.handle, h, idx.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), len(idx),
                                              paths.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))))
                 rows_out = np.zeros((len(idx), ncols, 4), dtype=np.uint64)
-                c.check(c.lib.ss_rows_gather(c.handle, ctypes.c_void_p(all_lde[first].data_ptr()), N, ncols,
+                c.check(c.lib.ss_rows_gather(c.handle, ctypes.c_void_p(all_lde[first].data_ptr()), S, ncols,
                                              idx.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), len(idx), rows_out.ctypes.data_as(ctypes.c_void_p)))
                 res.opened_bytes += paths.nbytes + rows_out.nbytes
             for handle, layer_evals, ls in layers:
