@@ -61,3 +61,67 @@ def test_constant_folding_and_cse():
     prog = compile_program(e, 3, 1, challenges=[2])
     # (t + 6) is shared, Challenge^5 folds to the constant 32
     assert prog.n_trace_taps == 1 and prog.n_mul == 1
+
+
+def test_small_coefficients_become_addition_chains():
+    """|c| <= 16 costs raw additions, not a multiplication; the emulator checks every bound on the way."""
+    rng = np.random.default_rng(8)
+    log_n, log_b = 4, 1
+    N = 1 << (log_n + log_b)
+    lde_int = [[int.from_bytes(rng.bytes(31), "big") for _ in range(N)] for _ in range(3)]
+    a, b, c = Trace(0, 0), Trace(1, 1), Trace(2, 0)
+    e = (Constant(2) * a - Constant(3) * b + Constant(16) * c * a - Constant(10) * (a * b) + Constant(P - 6) * c) * (a - Constant(13) * b)
+    prog = compile_program(e, log_n, log_b)
+    assert prog.n_mul == 3                                   # c*a, a*b and the outer product only
+    for i in range(N):
+        assert run_blob(prog.blob, i, lde_int, log_n + log_b) == eval_expr(e, i, lde_int, log_n, log_b, [], [], [0])
+
+
+def test_structure_hash_ignores_size_and_values():
+    """The hash that selects a build-time specialised kernel depends on the program's structure only: not on the
+    trace length, the challenge draw or the constants (tools/gen_ce_kernels.py relies on this)."""
+    import random
+
+    from sandstorm_b200.air.layouts import load_layout
+    from sandstorm_b200.air.program import structure_hash, tap_reach
+
+    L = load_layout("recursive")
+    hashes = set()
+    for log_n, seed in ((13, 1), (14, 2), (16, 3)):
+        rnd = random.Random(seed)
+        prog = compile_program(L.composition(1 << log_n, inv_x_minus_one_col=L.num_columns + 2), log_n, 1, [rnd.randrange(P) for _ in range(L.n_challenges())],
+                               [rnd.randrange(P) for _ in range(L.n_hints())], [rnd.randrange(P)], with_tables=False)
+        hashes.add(structure_hash(prog.blob))
+        reach = tap_reach(prog.blob, log_n + 1)
+        assert max(hi for _, hi in reach.values()) == 2 * L.max_offset and min(lo for lo, _ in reach.values()) >= -2 * 16
+    assert len(hashes) == 1
+    other = compile_program(L.composition(1 << 13), 13, 1, [1] * L.n_challenges(), [2] * L.n_hints(), [3], with_tables=False)
+    assert structure_hash(other.blob) not in hashes
+
+
+def test_deep_quotient_program_matches_definition():
+    """deep_expr_shifted (regrouped by column, shifted reads of u = 1/(x - z), v = 1/(x - z^ce)) == the definition
+    sum a_t (T(x) - y_t) / (x - z g^off), row by row, through the emulator of the device interpreter."""
+    import random
+
+    from sandstorm_b200.air.deep import deep_expr_shifted, deep_terms
+
+    rnd = random.Random(3)
+    log_n, b = 5, 1
+    n, N = 1 << log_n, 1 << (log_n + b)
+    g, w = pow(3, (P - 1) // n, P), pow(3, (P - 1) // N, P)
+    ncol, ce = 3, 2
+    lde = [[rnd.randrange(P) for _ in range(N)] for _ in range(ncol + ce)]
+    z, alpha = rnd.randrange(P), rnd.randrange(P)
+    zc = pow(z, ce, P)
+    taps = [(c, off) for c in range(ncol) for off in (0, 1, 2, 5, 7)[: 3 + c]]
+    tt, ct = deep_terms(taps, [rnd.randrange(P) for _ in taps], [rnd.randrange(P) for _ in range(ce)], ncol, alpha, P)
+    u = [pow(3 * pow(w, i, P) - z, -1, P) for i in range(N)]
+    v = [pow(3 * pow(w, i, P) - zc, -1, P) for i in range(N)]
+    prog = compile_program(deep_expr_shifted(tt, ct, ncol + ce, ncol + ce + 1, g, P), log_n, b)
+    assert prog.n_dot >= ncol
+    for i in range(N):
+        x = 3 * pow(w, i, P) % P
+        want = (sum(a * (lde[c][i] - y) * pow(x - z * pow(g, off, P), -1, P) for c, off, y, a in tt)
+                + sum(a * (lde[c][i] - y) * pow(x - zc, -1, P) for c, y, a in ct)) % P
+        assert run_blob(prog.blob, i, lde + [u, v], log_n + b) == want
