@@ -164,6 +164,12 @@ ss_status ss_ood_eval(ss_ctx *ctx, ss_field field, const void *d_trace_cols, uin
                       const int32_t *h_cols, const uint64_t *h_offsets, size_t n_evals, const void *h_z,
                       uint64_t row_begin, uint64_t row_count, void *h_out);
 
+/* ------------------------------------------------------------------ proof of work (§8 f.3)
+ * PublicCoin::grind_proof_of_work (crypto/src/public_coin/solidity.rs:120-141 with hash_kind 0 = Keccak-256,
+ * cairo.rs:133-154 with hash_kind 1 = Blake2s-256): the SMALLEST nonce >= 1 whose hash
+ * H(H(0x0123456789ABCDED || digest || bits) || nonce_be) starts with `bits` zero bits.  Synchronises. */
+ss_status ss_pow_grind(ss_ctx *ctx, int hash_kind, const uint8_t digest[32], int bits, uint64_t *nonce_out);
+
 /* ------------------------------------------------------------------ constraint evaluation (§8 a4-a7)
  * Evaluates a compiled composition-constraint program (the Expr DAG of
  * AirConfig::composition_constraint, layouts/src/recursive/air.rs:1184-1200, flattened by the host
