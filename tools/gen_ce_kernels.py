@@ -106,7 +106,7 @@ def programs():
     """(name, blob, resident CTAs per SM) for every program specialised at build time."""
     rnd = random.Random(0xB200)
     out = []
-    for layout, log_n in (("starknet", 18), ("recursive", 14)):
+    for layout, log_n in (("starknet", 18), ("recursive", 14), ("plain", 10)):
         L = load_layout(layout)
         C, n = L.num_columns, 1 << log_n
         ce = 2
