@@ -267,11 +267,11 @@ class HotPathProver:
         alpha = self._draw()
         t_terms, c_terms = deep_terms(taps, res.ood_trace, res.ood_composition, self.comp_col, alpha, P)
         # (the sub-coset evaluation below reads u and v only at rows that are multiples of the blowup)
-        deep_prog = compile_program(deep_expr_shifted(t_terms, c_terms, self.u_col, self.v_col, self.g, P), self.log_n, b)
-        if world == 1:
+        if world == 1:                                   # (launched first: the GPU works while the host compiles)
             inv_x_minus_c(all_lde[self.u_col], _mont(z), c, log_row_step=b)
             inv_x_minus_c(all_lde[self.v_col], _mont(zc), c, log_row_step=b)
-        else:
+        deep_prog = compile_program(deep_expr_shifted(t_terms, c_terms, self.u_col, self.v_col, self.g, P), self.log_n, b)
+        if world > 1:
             reach = tap_reach(deep_prog.blob, self.log_n + b)
             for col, point in ((self.u_col, z), (self.v_col, zc)):
                 lo_t, hi_t = reach.get(col, (0, 0))
