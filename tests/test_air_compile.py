@@ -125,3 +125,33 @@ def test_deep_quotient_program_matches_definition():
         want = (sum(a * (lde[c][i] - y) * pow(x - z * pow(g, off, P), -1, P) for c, off, y, a in tt)
                 + sum(a * (lde[c][i] - y) * pow(x - zc, -1, P) for c, y, a in ct)) % P
         assert run_blob(prog.blob, i, lde + [u, v], log_n + b) == want
+
+
+@pytest.mark.parametrize("name,log_n", [("plain", 8), ("recursive", 15), ("starknet", 19)])
+def test_generated_kernel_registry_matches_prover_programs(name, log_n):
+    """The registry written by tools/gen_ce_kernels.py (csrc/ce_gen.cuh, built by __graft_entry__.build()) must contain the
+    structure hash of the programs the prover compiles — at another trace length and challenge draw than the generator's —
+    otherwise ss_constraint_eval silently runs the interpreter instead of the specialised kernels."""
+    import os
+    import random
+    import re
+
+    from sandstorm_b200.air.deep import deep_expr_shifted, deep_terms
+    from sandstorm_b200.air.layouts import load_layout
+    from sandstorm_b200.air.program import structure_hash
+
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "sandstorm_b200", "csrc", "ce_gen.cuh")
+    if not os.path.exists(path):
+        import __graft_entry__ as g
+
+        g.build()
+    registry = {int(h, 16): n for h, n in re.findall(r"\{0x([0-9a-f]{16})ull, ce_gen_(\w+),", open(path).read())}
+    L = load_layout(name)
+    C, ce, n = L.num_columns, 2, 1 << log_n
+    rnd = random.Random(991 + log_n)
+    comp = compile_program(L.composition(n, inv_x_minus_one_col=C + ce), log_n, 1, [rnd.randrange(P) for _ in range(L.n_challenges())],
+                           [rnd.randrange(P) for _ in range(L.n_hints())], [rnd.randrange(P)], with_tables=False)
+    tt, ct = deep_terms(L.taps(), [rnd.randrange(P) for _ in L.taps()], [rnd.randrange(P) for _ in range(ce)], C, rnd.randrange(P), P)
+    deep = compile_program(deep_expr_shifted(tt, ct, C + ce + 1, C + ce + 2, pow(3, (P - 1) // n, P), P), log_n, 1, with_tables=False)
+    assert registry.get(structure_hash(comp.blob), "").startswith(f"{name}_composition")
+    assert registry.get(structure_hash(deep.blob), "").startswith(f"{name}_deep")

@@ -70,6 +70,43 @@ def test_two_rank_sharding_matches_single_process(oracle):
         assert combined == want_root
 
 
+def _ranges_worker(rank, world, port, full_np, halo, q):
+    from sandstorm_b200 import parallel
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        full = torch.from_numpy(full_np)
+        n_cols, N = full.shape[0], full.shape[1]
+        mine = torch.zeros_like(full)
+        for j in parallel.owned_columns(n_cols, rank, world):
+            mine[j] = full[j]                                  # a column is complete on its owner only
+        parallel.share_row_ranges(mine, world, rank, halo)
+        lo, hi = parallel.row_range(N, rank, world)
+        need = [(lo + k) % N for k in range(hi - lo + halo)]
+        q.put((rank, bool(torch.equal(mine[:, need], full[:, need]))))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,halo", [(4, 7), (4, 0), (2, 40)])
+def test_row_range_exchange(world, halo):
+    """share_row_ranges with 4 ranks / wrap-around halo / a halo larger than a rank's range (falls back to whole columns)."""
+    rng = np.random.default_rng(world + halo)
+    full = rng.integers(0, 2**62, size=(5, 64, 4), dtype=np.int64)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ranges_worker, args=(r, world, port, full, halo, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=90) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in results), results
+
+
 def test_ownership_helpers():
     from sandstorm_b200 import parallel
 
