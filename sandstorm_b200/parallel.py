@@ -75,6 +75,40 @@ def share_row_ranges(matrix: torch.Tensor, world: int, rank: int, halo: int) -> 
         req.wait()
 
 
+def redistribute(column: torch.Tensor, world: int, rank: int, chunk: int, to_cyclic: bool) -> None:
+    """Ownership exchange of the row-sharded four-step NTT (tools/ntt_model.py), in place on a full-size
+    column [N, limbs] of which this rank owns
+        contiguous   : positions p with p // (N / world) == rank, or
+        chunk-cyclic : positions p with (p // chunk) % world == rank.
+    to_cyclic=True turns the first into the second (before the strided passes), False the reverse (before / after the
+    contiguous pass).  Viewed as [world, K, world, chunk, limbs] the two maps are the first and the third axis, so the
+    exchange is a block transpose: rank r sends x[r, :, d] to d and receives x[s, :, r] from s (and the mirror image)."""
+    if world == 1:
+        return
+    N = column.shape[0]
+    if N % (world * world * chunk):
+        raise ValueError("column length must be a multiple of world^2 * chunk")
+    x = column.view(world, N // (world * world * chunk), world, chunk, *column.shape[1:])
+    sends, recvs, ops = [], [], []
+    for other in range(world):
+        if other == rank:
+            continue
+        src = x[rank, :, other] if to_cyclic else x[other, :, rank]
+        buf = src.contiguous()
+        landing = torch.empty_like(buf)
+        sends.append(buf)
+        recvs.append((other, landing))
+        ops.append(dist.P2POp(dist.isend, buf, other))
+        ops.append(dist.P2POp(dist.irecv, landing, other))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    for other, landing in recvs:
+        if to_cyclic:
+            x[other, :, rank] = landing
+        else:
+            x[rank, :, other] = landing
+
+
 def gather_subroots(my_root: bytes, world: int, device) -> list[bytes]:
     """All-gather of the per-rank sub-tree roots, in rank (= row) order."""
     if world == 1:

@@ -107,6 +107,47 @@ def test_row_range_exchange(world, halo):
     assert all(ok for _, ok in results), results
 
 
+def _redistribute_worker(rank, world, port, full_np, chunk, q):
+    from sandstorm_b200 import parallel
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        full = torch.from_numpy(full_np)
+        N = full.shape[0]
+        pos = torch.arange(N)
+        contig = (pos // (N // world)) == rank
+        cyclic = ((pos // chunk) % world) == rank
+        mine = torch.where(contig[:, None], full, torch.full_like(full, -1))      # -1 marks positions this rank does not own
+        parallel.redistribute(mine, world, rank, chunk, to_cyclic=True)
+        ok1 = bool(torch.equal(mine[cyclic], full[cyclic]))
+        mine[~cyclic] = -1                                                         # forget what is no longer owned
+        parallel.redistribute(mine, world, rank, chunk, to_cyclic=False)
+        ok2 = bool(torch.equal(mine[contig], full[contig]))
+        q.put((rank, ok1, ok2))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,chunk", [(2, 4), (4, 2)])
+def test_four_step_ownership_exchange(world, chunk):
+    """redistribute(): contiguous -> chunk-cyclic -> contiguous ownership of a column (the all-to-alls of the planned
+    row-sharded NTT), every owned position arrives and nothing else is needed."""
+    rng = np.random.default_rng(world * 10 + chunk)
+    full = rng.integers(0, 2**62, size=(256, 4), dtype=np.int64)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_redistribute_worker, args=(r, world, port, full, chunk, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=90) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(a and b for _, a, b in results), results
+
+
 def test_ownership_helpers():
     from sandstorm_b200 import parallel
 
