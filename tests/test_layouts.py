@@ -33,7 +33,7 @@ def test_layout_shapes_match_reference():
     assert all(off >= 0 for L in (plain, rec, stark) for _, off in L.taps())
 
 
-@pytest.mark.parametrize("name,log_n", [("plain", 5), ("recursive", 11)])
+@pytest.mark.parametrize("name,log_n", [("plain", 5), ("recursive", 11), ("starknet", 15)])
 def test_compiled_layout_matches_tree_evaluator(name, log_n):
     L = load_layout(name)
     rnd = random.Random(log_n)
@@ -43,11 +43,21 @@ def test_compiled_layout_matches_tree_evaluator(name, log_n):
     ch = [rnd.randrange(P) for _ in range(L.n_challenges())]
     hints = [rnd.randrange(P) for _ in range(L.n_hints())]
     alpha = [rnd.randrange(P)]
-    expr = L.composition(n)
-    prog = compile_program(expr, log_n, 1, ch, hints, alpha)
-    assert prog.n_slots <= 64
-    for i in (0, 1, 17, N // 2 + 3, N - 1):
-        assert run_blob(prog.blob, i, lde_int, log_n + 1) == eval_expr(expr, i, lde_int, log_n, 1, ch, hints, alpha)
+    # with the auxiliary column w = 1/(x - 1) the boundary denominators are shifted reads (what the prover compiles);
+    # without it they are inverted per row: both forms must agree with the tree evaluator, bounds asserted by the emulator
+    w = pow(3, (P - 1) // N, P)
+
+    class LazyW:                                     # w[i] = 1 / (x_i - 1), computed on access
+        def __getitem__(self, i):
+            return pow(3 * pow(w, i % N, P) - 1, -1, P)
+
+    variants = [(L.composition(n), lde_int), (L.composition(n, inv_x_minus_one_col=L.num_columns), lde_int + [LazyW()])]
+    rows = (0, 1, 17, N // 2 + 3, N - 1) if name != "starknet" else (0, 5, N - 1)
+    for expr, cols in variants:
+        prog = compile_program(expr, log_n, 1, ch, hints, alpha)
+        assert prog.n_slots <= 64
+        for i in rows:
+            assert run_blob(prog.blob, i, cols, log_n + 1) == eval_expr(L.composition(n), i, lde_int, log_n, 1, ch, hints, alpha)
 
 
 def test_trace_length_validation():
