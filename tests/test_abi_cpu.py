@@ -56,3 +56,18 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text and "liboracle" not in text, f
+
+
+def test_header_is_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/sandstorm_b200.h must compile as C99 (what cgo / bindgen / a Rust build.rs
+    feed to their C front end) as well as C++, with no CUDA or torch types in the signatures."""
+    import subprocess
+
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "sandstorm_b200.h"\nint main(void) { ss_ctx *c = 0; (void)c; return (int)SS_OK; }\n')
+    inc = os.path.join(ROOT, "include")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, str(src)])
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c++", "-I", inc, str(src)])
+    text = open(os.path.join(inc, "sandstorm_b200.h")).read()
+    code = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    assert not re.search(r"cudaStream_t|cudaError_t|#include\s*<cuda|at::|torch::", code), "CUDA / torch types leak into the C ABI"
