@@ -120,7 +120,9 @@ ss_status ss_merkle_leaves(ss_ctx *ctx, const ss_tree *tree, const uint64_t *h_i
 ss_status ss_merkle_open(ss_ctx *ctx, const ss_tree *tree, const uint64_t *h_indices, size_t n,
                          uint8_t *h_paths /* n * log_rows * 32 */);
 /* Root of a row-sharded commitment: 2^log_count sub-tree roots (one per GPU row range, in row
- * order) -> root of the whole tree.  Byte-hash kinds only.  Synchronises. */
+ * order, as ss_merkle_root returns them) -> root of the whole tree.  For SS_TREE_FRIENDLY the combined
+ * levels are Pedersen (log_count <= N_FRIENDLY) and each sub-tree is built with n_friendly - log_count.
+ * Synchronises. */
 ss_status ss_merkle_combine(ss_ctx *ctx, ss_tree_kind kind, const uint8_t *h_subroots, int log_count, uint8_t root[32]);
 int ss_tree_log_rows(const ss_tree *tree);
 void ss_tree_free(ss_tree *tree);
