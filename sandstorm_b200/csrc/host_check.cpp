@@ -115,24 +115,6 @@ void hc_inv_chain(const uint32_t *a, uint32_t *out) {
 
 }  // extern "C"
 
-// ---- carry-free 28-bit-limb arithmetic (fp28.cuh) ----
-#include "fp28.cuh"
-extern "C" {
-void hc_f28_roundtrip(const uint32_t *a, uint32_t *out) { Fp x; std::memcpy(x.l, a, 32); Fp r = f28::to_fp(f28::from_fp(x)); std::memcpy(out, r.l, 32); }
-// out = limbs of mulc(a_limbs, const_from_mont(c_mont))
-void hc_f28_mulc(const uint32_t *a_limbs, const uint32_t *c_mont, uint32_t *out_limbs) {
-    F28 a; std::memcpy(a.l, a_limbs, 36);
-    Fp c; std::memcpy(c.l, c_mont, 32);
-    F28 r = f28::mulc(a, f28::const_from_mont(c), f28::mulk_literal());
-    std::memcpy(out_limbs, r.l, 36);
-}
-void hc_f28_weak_reduce(const uint32_t *a_limbs, uint32_t *out_limbs) { F28 a; std::memcpy(a.l, a_limbs, 36); F28 r = f28::weak_reduce(a); std::memcpy(out_limbs, r.l, 36); }
-void hc_f28_sub(const uint32_t *a, const uint32_t *b, int dit, uint32_t *out) {
-    F28 x, y; std::memcpy(x.l, a, 36); std::memcpy(y.l, b, 36);
-    F28 r = dit ? f28::sub_dit(x, y) : f28::sub_dif(x, y); std::memcpy(out, r.l, 36);
-}
-}
-
 // ---- Goldilocks single-limb arithmetic (goldilocks.cuh) ----
 #include "goldilocks.cuh"
 extern "C" {

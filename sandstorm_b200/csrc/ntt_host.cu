@@ -2,7 +2,6 @@
 // and the ss_ntt / ss_lde entry points (include/sandstorm_b200.h).
 #include "ctx.h"
 #include "ntt_fp252.cuh"
-#include "ntt_fp252_r28.cuh"
 #include <cstdlib>
 
 using namespace ss;
@@ -63,36 +62,6 @@ void fill_scale_hi(Fp *dst, size_t n, int log_n, int variant) {
     geometric(dst, n, fp::one(), fp::pow_u64(h, 4096));
 }
 
-// F28 table (12 words per entry, constants pre-scaled by 2^280) built from the same generators as the Fp tables
-ss_status cached_table28(ss_ctx *ctx, std::tuple<int, int, int> key, size_t n_entries,
-                         void (*fill)(Fp *dst, size_t n, int log_n, int variant), const uint32_t **out) {
-    std::get<0>(key) += 100;
-    auto it = ctx->tables.find(key);
-    if (it != ctx->tables.end()) { *out = static_cast<const uint32_t *>(it->second); return SS_OK; }
-    std::vector<Fp> tmp(n_entries);
-    fill(tmp.data(), n_entries, std::get<1>(key), std::get<2>(key));
-    std::vector<uint32_t> words(n_entries * F28_WORDS, 0u);
-    for (size_t i = 0; i < n_entries; ++i) {
-        const F28 c = f28::const_from_mont(tmp[i]);
-        for (int k = 0; k < 9; ++k) words[i * F28_WORDS + k] = c.l[k];
-    }
-    void *d = nullptr;
-    SS_CUDA_CHECK(ctx, cudaMalloc(&d, words.size() * 4));
-    SS_CUDA_CHECK(ctx, cudaMemcpy(d, words.data(), words.size() * 4, cudaMemcpyHostToDevice));
-    ctx->tables[key] = d;
-    *out = static_cast<const uint32_t *>(d);
-    return SS_OK;
-}
-
-// Experimental carry-free 28-bit-limb pass kernel (ntt_fp252_r28.cuh).  Bit-identical output, but measured
-// 30 % SLOWER than the radix-2^32 kernel on B200 (profiles/r01_ntt_radix28.md), so it is off unless
-// SS_NTT_RADIX28=1 is set in the environment.
-bool use_radix28() {
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("SS_NTT_RADIX28"); v = e ? atoi(e) : 0; }
-    return v != 0;
-}
-
 std::vector<int> plan_passes(int log_n) {
     if (log_n <= NTT_LOG_TILE) return {log_n};
     const int k = (log_n + NTT_LOG_TILE - 1) / NTT_LOG_TILE;
@@ -112,27 +81,6 @@ struct NttJob {
     int scale_variant;
     bool canon_out;
 };
-
-template <bool DIT>
-ss_status launch_pass28(ss_ctx *ctx, const NttPass28 &q, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        SS_CUDA_CHECK(ctx, cudaFuncSetAttribute(ntt_pass_kernel_r28<DIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT28_SMEM_BYTES));
-        configured = true;
-    }
-    const NttPass &p = q.base;
-    dim3 grid;
-    if (p.log_n < NTT_LOG_TILE) {
-        const int per_tile = 1 << (NTT_LOG_TILE - p.log_n);
-        grid = dim3((p.n_cols + per_tile - 1) / per_tile, 1, 1);
-    } else {
-        grid = dim3(1u << (p.log_n - NTT_LOG_TILE), p.n_cols, 1);
-    }
-    ntt_pass_kernel_r28<DIT><<<grid, NTT_THREADS, NTT28_SMEM_BYTES, st>>>(q);
-    ctx->launches++;
-    SS_CUDA_CHECK(ctx, cudaGetLastError());
-    return SS_OK;
-}
 
 template <bool DIT>
 ss_status launch_pass(ss_ctx *ctx, const NttPass &p, cudaStream_t st) {
@@ -174,19 +122,6 @@ ss_status run_ntt(ss_ctx *ctx, const NttJob &job, cudaStream_t st) {
         if (!is_const)
             if ((rc = cached_table(ctx, {T_SCALE_HI, job.log_n, job.scale_variant}, n <= 4096 ? 1 : n / 4096, fill_scale_hi, &sc_hi))) return rc;
     }
-    const bool r28 = use_radix28();
-    const uint32_t *t28_local = nullptr, *t28_lo = nullptr, *t28_hi = nullptr, *s28_lo = nullptr, *s28_hi = nullptr;
-    if (r28) {
-        if ((rc = cached_table28(ctx, {T_LOCAL, 12, inv}, 2048, fill_local, &t28_local))) return rc;
-        if ((rc = cached_table28(ctx, {T_LO, job.log_n, inv}, n < 4096 ? n : 4096, fill_lo, &t28_lo))) return rc;
-        if ((rc = cached_table28(ctx, {T_HI, job.log_n, inv}, n <= 4096 ? 1 : n / 4096, fill_hi, &t28_hi))) return rc;
-        if (job.pre_scale != SCALE_NONE || job.post_scale != SCALE_NONE) {
-            const bool is_const = job.pre_scale == SCALE_CONST || job.post_scale == SCALE_CONST;
-            if ((rc = cached_table28(ctx, {T_SCALE_LO, job.log_n, job.scale_variant}, is_const ? 1 : (n < 4096 ? n : 4096), fill_scale_lo, &s28_lo))) return rc;
-            if (!is_const)
-                if ((rc = cached_table28(ctx, {T_SCALE_HI, job.log_n, job.scale_variant}, n <= 4096 ? 1 : n / 4096, fill_scale_hi, &s28_hi))) return rc;
-        }
-    }
     const std::vector<int> passes = plan_passes(job.log_n);
     const int np = (int)passes.size();
     int log_b = job.dit ? 0 : job.log_n;
@@ -213,15 +148,7 @@ ss_status run_ntt(ss_ctx *ctx, const NttJob &job, cudaStream_t st) {
         p.scale_lo = sc_lo;
         p.scale_hi = sc_hi;
         p.canon_out = (last && job.canon_out) ? 1 : 0;
-        if (r28) {
-            NttPass28 q28;
-            q28.base = p;
-            q28.tw_local = t28_local; q28.tw_lo = t28_lo; q28.tw_hi = t28_hi; q28.scale_lo = s28_lo; q28.scale_hi = s28_hi;
-            q28.K = f28::mulk_literal();
-            rc = job.dit ? launch_pass28<true>(ctx, q28, st) : launch_pass28<false>(ctx, q28, st);
-        } else {
-            rc = job.dit ? launch_pass<true>(ctx, p, st) : launch_pass<false>(ctx, p, st);
-        }
+        rc = job.dit ? launch_pass<true>(ctx, p, st) : launch_pass<false>(ctx, p, st);
         if (rc) return rc;
         if (!job.dit) log_b -= L;
     }

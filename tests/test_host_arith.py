@@ -82,49 +82,3 @@ def test_inverse_and_constants(hc):
     assert val(out) == 12345 * R % P
 
 
-# ---- carry-free 28-bit-limb arithmetic (fp28.cuh; experimental NTT variant, SS_NTT_RADIX28=1) ----------------
-def limbs28(v, n=9):
-    out = [(v >> (28 * i)) & (2**28 - 1) for i in range(n - 1)]
-    return (ctypes.c_uint32 * n)(*(out + [v >> (28 * (n - 1))]))
-
-
-def val28(a):
-    return sum(int(a[i]) << (28 * i) for i in range(9))
-
-
-def test_f28_roundtrip_mulc_and_bounds(hc):
-    rnd = random.Random(3)
-    for v in EDGE + [rnd.randrange(2**256) for _ in range(2000)]:
-        assert call(hc.hc_f28_roundtrip, v) == v
-    rinv = pow(R, -1, P)
-    for _ in range(3000):
-        # operand: lazy limbs (each < 2^32), value < 2^256; constant: canonical Montgomery form
-        a = (ctypes.c_uint32 * 9)(*([rnd.randrange(2**32) for _ in range(8)] + [rnd.randrange(2**28)]))
-        while val28(a) >= 2**256:
-            a[8] = rnd.randrange(2**27)
-        c = rnd.randrange(P)
-        out = (ctypes.c_uint32 * 9)()
-        hc.hc_f28_mulc(a, arr(c * R % P), out)
-        r = val28(out)
-        assert all(out[i] < 2**28 for i in range(8))
-        assert r % P == val28(a) * c % P                      # data stays in the R = 2^256 form
-        assert r < P + 2**228
-
-
-def test_f28_weak_reduce_and_biased_sub(hc):
-    rnd = random.Random(4)
-    for _ in range(5000):
-        a = (ctypes.c_uint32 * 9)(*[rnd.randrange(int(2**31.3)) for _ in range(9)])
-        if val28(a) >= 2**256:
-            a[8] = rnd.randrange(2**27)
-        out = (ctypes.c_uint32 * 9)()
-        hc.hc_f28_weak_reduce(a, out)
-        assert all(out[i] < 2**28 for i in range(8))
-        assert val28(out) % P == val28(a) % P and val28(out) < 2**252 + 9 * 2**224
-    for dit, bound_b, k in ((0, 2**30, 9), (1, 2**28, 3)):
-        for _ in range(3000):
-            a = (ctypes.c_uint32 * 9)(*[rnd.randrange(2**30) for _ in range(9)])
-            b = (ctypes.c_uint32 * 9)(*[rnd.randrange(bound_b) for _ in range(9)])
-            out = (ctypes.c_uint32 * 9)()
-            hc.hc_f28_sub(a, b, dit, out)
-            assert val28(out) == val28(a) - val28(b) + k * P      # no borrow anywhere: exact integer identity
