@@ -11,7 +11,8 @@ class Expr:
     _table: dict = {}
 
     def __new__(cls, op, *args):
-        key = (op,) + tuple(a if not isinstance(a, Expr) else id(a) for a in args)
+        # (a tracked constant, air/symbolic.py, is keyed by its tape so that it never aliases a plain integer)
+        key = (op,) + tuple(id(a) if isinstance(a, Expr) else (a.cons_key() if hasattr(a, "cons_key") else a) for a in args)
         hit = cls._table.get(key)
         if hit is not None:
             return hit

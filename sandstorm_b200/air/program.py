@@ -24,7 +24,10 @@ evaluator) is split here between host and device:
 Program blob, version 2 (little-endian u32 words unless noted):
   [0] magic 'SSCP'  [1] version  [2] n_words (16-byte code words)  [3] n_consts  [4] n_tables  [5] n_slots
   [6] log_n (trace) [7] log_blowup  [8] n_taps  [9..15] reserved
-  then n_tables x (log_period, offset in elements), padded to an even count
+  then n_tables x (log_period | (scale + 1) << 8, offset in elements), padded to an even count
+       scale = index of a constant the stored table has to be multiplied by before use (ss_constraint_eval does it on
+       the device when it uploads the blob): a table that is a challenge-dependent coefficient times a
+       challenge-independent periodic function keeps its precomputed values, and only the coefficient is patched
   then n_taps x (column, row offset mod N in LDE rows), padded to an even count
   then n_words x 4 words of code     then consts (32 B each)   then table data (32 B each)
 Code word:  (op | dst << 8 | n << 16, A, B, 0);  a DOT is followed by ceil(n / 2) words (A0, B0, A1, B1).
@@ -39,10 +42,11 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from .expr import Expr, P
+from .symbolic import Sym, Tape, replay, value_of
 
 R = 2**256
 MAGIC = 0x50435353          # 'SSCP'
-VERSION = 2
+VERSION = 3
 MAX_TABLE_LOG = 17
 GENERATOR = 3
 
@@ -54,6 +58,28 @@ FULL = 0    # period marker for row-dependent nodes
 def _mont_limbs(v: int) -> list[int]:
     m = v % P * R % P
     return [(m >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)]
+
+
+def _ntt(a: list, root: int) -> list:
+    """plain radix-2 transform: out[j] = sum_m a[m] * root^(j m), len(a) a power of two, root of that order."""
+    n = len(a)
+    if n == 1:
+        return a
+    bits = n.bit_length() - 1
+    a = [a[int(f"{i:0{bits}b}"[::-1], 2)] for i in range(n)]
+    size = 2
+    while size <= n:
+        wn, half = pow(root, n // size, P), size // 2
+        tw, t = [1] * half, 1
+        for j in range(half):
+            tw[j] = t
+            t = t * wn % P
+        for start in range(0, n, size):
+            for j in range(half):
+                u, v = a[start + j], a[start + j + half] * tw[j] % P
+                a[start + j], a[start + j + half] = (u + v) % P, (u - v) % P
+        size *= 2
+    return a
 
 
 @dataclass
@@ -71,6 +97,35 @@ class CompiledProgram:
     n_red: int = 0
     n_dot: int = 0
     n_inv: int = 0
+
+
+@dataclass
+class ProgramTemplate:
+    """A constraint program compiled ahead of the proof on tracked challenges (air/symbolic.py): everything but the
+    values of the challenge-dependent constants.  `patch` substitutes the real challenges / hints / composition
+    coefficients — a tape replay over a few thousand field operations plus one copy of the blob — and is the only
+    part of the compilation on the critical path of a prove (between the extension-trace commitment and constraint
+    evaluation).  The result is bit-identical to compiling with the values directly: same code, same constants."""
+    head: bytes                      # header, table descriptors, taps, code (padded to 32 bytes)
+    const_refs: list                 # per constant: canonical int or ('s', tape slot)
+    tape_ops: list
+    n_inputs: tuple                  # (n_challenges, n_hints, n_coeffs)
+    table_bytes: bytes
+    stats: "CompiledProgram"
+
+    def patch(self, challenges=(), hints=(), composition_coeffs=(0,)) -> CompiledProgram:
+        nc, nh, nk = self.n_inputs
+        inputs = list(challenges) + list(hints) + list(composition_coeffs)
+        if (len(challenges), len(hints), len(composition_coeffs)) != (nc, nh, nk):
+            raise ValueError(f"template expects {nc} challenges, {nh} hints, {nk} composition coefficients")
+        vals = replay(self.tape_ops, inputs)
+        consts = [vals[r[1]] if isinstance(r, tuple) else r for r in self.const_refs]
+        body = np.array([l for v in consts for l in _mont_limbs(v)], dtype=np.uint64).tobytes() if consts else b""
+        st = self.stats
+        return CompiledProgram(blob=b"".join((self.head, body, self.table_bytes)), n_instr=st.n_instr, n_consts=st.n_consts,
+                               n_tables=st.n_tables, n_slots=st.n_slots, n_mul=st.n_mul, n_addsub=st.n_addsub,
+                               n_trace_taps=st.n_trace_taps, n_batch_inv=st.n_batch_inv, table_sizes=st.table_sizes, n_red=st.n_red,
+                               n_dot=st.n_dot, n_inv=st.n_inv)
 
 
 class _Lower:
@@ -218,10 +273,20 @@ class _Lower:
             vals = powers(1, T)
         elif op == "periodic":
             coeffs, interval = e.args
-            ys = powers(self.n // interval, T)
-            vals = [0] * T
-            for c in reversed(coeffs):
-                vals = [(v * y + c) % P for v, y in zip(vals, ys)]
+            k = self.n // interval
+            if len(coeffs) <= 16 or len(coeffs) > T:
+                ys = powers(k, T)
+                vals = [0] * T
+                for c in reversed(coeffs):
+                    vals = [(v * y + c) % P for v, y in zip(vals, ys)]
+            else:
+                # the T points are y_j = 3^k * W^j with W = w^k of order T: one size-T transform of the coefficients
+                # scaled by (3^k)^m instead of len(coeffs) * T Horner steps
+                shift, acc, a = pow(GENERATOR, k, P), 1, []
+                for c in coeffs:
+                    a.append(c * acc % P)
+                    acc = acc * shift % P
+                vals = _ntt(a + [0] * (T - len(a)), pow(self.w, k % self.N, P))
         else:
             args = [self.table_values(a, memo) for a in e.args]
             a = args[0]
@@ -269,6 +334,7 @@ SMALL_COEFF = 16                     # |c| <= this: c * A is a short chain of ad
 
 def _small(c: int) -> int:
     """signed value of a coefficient when it is a small integer (2 <= |s| <= SMALL_COEFF), else 0."""
+    c = value_of(c)
     if 2 <= c <= SMALL_COEFF:
         return c
     if 2 <= P - c <= SMALL_COEFF:
@@ -313,9 +379,23 @@ class _Graph:
 LEAF_KINDS = ("const", "table", "trace")
 
 
+def compile_template(expr: Expr, log_n: int, log_blowup: int, n_challenges: int = 0, n_hints: int = 0, n_coeffs: int = 1,
+                     max_slots: int = 256, regroup: bool = True, with_tables: bool = True, seed: int = 0x5EED) -> ProgramTemplate:
+    """Compiles `expr` with the challenges / hints / composition coefficients left open (see ProgramTemplate).  The
+    reference draw that steers the structural decisions is generic (seeded random field elements), so the structure is
+    the one every real draw has, including draws whose hints happen to be 0 or 1."""
+    import random
+
+    rnd, tape = random.Random(seed), Tape()
+    syms = [tape.input(rnd.randrange(2, P)) for _ in range(n_challenges + n_hints + n_coeffs)]
+    return compile_program(expr, log_n, log_blowup, syms[:n_challenges], syms[n_challenges:n_challenges + n_hints],
+                           syms[n_challenges + n_hints:], max_slots, regroup, with_tables, _tape=tape)
+
+
 def compile_program(expr: Expr, log_n: int, log_blowup: int, challenges=(), hints=(), composition_coeffs=(0,),
-                    max_slots: int = 256, regroup: bool = True, with_tables: bool = True) -> CompiledProgram:
-    """expr: the composition constraint (or any Expr).  challenges / hints / composition_coeffs: canonical ints."""
+                    max_slots: int = 256, regroup: bool = True, with_tables: bool = True, _tape: Tape | None = None):
+    """expr: the composition constraint (or any Expr).  challenges / hints / composition_coeffs: canonical ints.
+    (With _tape — compile_template — they are tracked symbols and the result is a ProgramTemplate.)"""
     import sys
     sys.setrecursionlimit(max(sys.getrecursionlimit(), 200000))
     lw = _Lower(log_n, log_blowup, list(challenges), list(hints), list(composition_coeffs))
@@ -794,16 +874,60 @@ def compile_program(expr: Expr, log_n: int, log_blowup: int, challenges=(), hint
         raise ValueError(f"program needs {n_slots} value slots, the kernel has {max_slots}")
 
     # ---- 5. serialise --------------------------------------------------------------------------------------
+    # A table whose expression involves a tracked constant must have the form  constant * (challenge-independent table):
+    # the values of the second factor are stored and the constant becomes the table's device-side scale.
+    sym_memo: dict = {}
+
+    def has_sym(e: Expr) -> bool:
+        hit = sym_memo.get(e)
+        if hit is None:
+            hit = isinstance(e.args[0], Sym) if e.op == "const" else any(has_sym(a) for a in e.args if isinstance(a, Expr))
+            sym_memo[e] = hit
+        return hit
+
+    def split_sym(e: Expr):
+        """e == factor * base with `factor` the product of the tracked constants among e's multiplicative factors
+        (None = 1) and `base` challenge-independent (None = 1)."""
+        if not has_sym(e):
+            return None, e
+        if e.op == "const":
+            return e.args[0], None
+        if e.op in ("mul", "div"):
+            (fa, ba), (fb, bb) = split_sym(e.args[0]), split_sym(e.args[1])
+            if e.op == "div":
+                fb = pow(fb, -1, P) if fb is not None else None
+                bb = Expr("div", Expr("const", 1), bb) if bb is not None else None
+            f = fa if fb is None else (fb if fa is None else fa * fb % P)
+            b = ba if bb is None else (bb if ba is None else Expr("mul", ba, bb))
+            return f, b
+        if e.op == "neg":
+            f, b = split_sym(e.args[0])
+            return (f, Expr("neg", b)) if b is not None else (-f % P, None)
+        raise NotImplementedError("a periodic table depends on the challenges other than through a constant factor")
+
     table_memo: dict = {}
-    # with_tables=False (build-time code generation): only the shape of the tables is needed
-    table_vals = [lw.table_values(e, table_memo) if with_tables else [0] * lw.period(e) for e in tables]
+    table_vals, table_scale = [], []
+    for e in tables:
+        scale, base = None, e
+        if has_sym(e):
+            f, base = split_sym(e)
+            scale = const_id(f)
+            if base is None:
+                base = Expr("const", 1)
+        T = lw.period(e)
+        # with_tables=False (build-time code generation): only the shape of the tables is needed
+        vals = lw.table_values(base, table_memo) if with_tables else [0] * T
+        if len(vals) != T:
+            vals = vals * (T // len(vals))
+        table_vals.append(vals)
+        table_scale.append(scale)
     del table_memo
     if log_n + log_blowup > 32:
         raise ValueError("tap offsets are stored as 32-bit row indices")
     words = [MAGIC, VERSION, len(code), len(consts), len(tables), max(n_slots, 1), log_n, log_blowup, len(tap_list), 0, 0, 0, 0, 0, 0, 0]
     off = 0
-    for t in table_vals:
-        words += [len(t).bit_length() - 1, off]
+    for t, sc in zip(table_vals, table_scale):
+        words += [(len(t).bit_length() - 1) | ((sc + 1) << 8 if sc is not None else 0), off]
         off += len(t)
     if len(tables) & 1:
         words += [0, 0]                      # keep the following areas 16-byte aligned
@@ -816,11 +940,19 @@ def compile_program(expr: Expr, log_n: int, log_blowup: int, challenges=(), hint
     head = struct.pack(f"<{len(words)}I", *words)
     if len(head) % 32:
         head += b"\0" * (32 - len(head) % 32)
-    felts = [l for v in consts for l in _mont_limbs(v)] + [l for t in table_vals for v in t for l in _mont_limbs(v)]
-    body = np.array(felts, dtype=np.uint64).tobytes() if felts else b""
-    return CompiledProgram(blob=head + body, n_instr=len(code), n_consts=len(consts), n_tables=len(tables), n_slots=max(n_slots, 1),
-                           n_mul=stats["mul"], n_addsub=stats["addsub"], n_trace_taps=stats["trace"], n_batch_inv=len(inv_nodes),
-                           table_sizes=[len(t) for t in table_vals], n_red=stats["red"], n_dot=stats["dot"], n_inv=stats["inv"])
+    tfelts = [l for t in table_vals for v in t for l in _mont_limbs(v)]
+    table_bytes = np.array(tfelts, dtype=np.uint64).tobytes() if tfelts else b""
+    stats_obj = CompiledProgram(blob=b"", n_instr=len(code), n_consts=len(consts), n_tables=len(tables), n_slots=max(n_slots, 1),
+                                n_mul=stats["mul"], n_addsub=stats["addsub"], n_trace_taps=stats["trace"], n_batch_inv=len(inv_nodes),
+                                table_sizes=[len(t) for t in table_vals], n_red=stats["red"], n_dot=stats["dot"], n_inv=stats["inv"])
+    if _tape is not None:
+        ops, refs = _tape.compact(consts)
+        return ProgramTemplate(head=head, const_refs=refs, tape_ops=ops,
+                               n_inputs=(len(lw.challenges), len(lw.hints), len(lw.coeffs)), table_bytes=table_bytes, stats=stats_obj)
+    assert not any(isinstance(v, Sym) for v in consts)
+    felts = [l for v in consts for l in _mont_limbs(v)]
+    stats_obj.blob = head + (np.array(felts, dtype=np.uint64).tobytes() if felts else b"") + table_bytes
+    return stats_obj
 
 
 def structure_hash(blob: bytes) -> int:

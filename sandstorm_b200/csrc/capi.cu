@@ -1,5 +1,6 @@
 // Context, memory helpers and error plumbing of the C ABI (include/sandstorm_b200.h).
 #include "ctx.h"
+#include <cstring>
 
 using namespace ss;
 
@@ -44,6 +45,27 @@ void dev_free(ss_ctx *ctx, void *ptr) {
     auto it = ctx->pool_size.find(ptr);
     if (it == ctx->pool_size.end()) { cudaFree(ptr); return; }
     ctx->pool_free.emplace(it->second, ptr);
+}
+
+ss_status stage_upload(ss_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, cudaStream_t st) {
+    if (ctx->stage_busy) {
+        SS_CUDA_CHECK(ctx, cudaEventSynchronize(ctx->stage_done));
+        ctx->stage_busy = false;
+    }
+    if (bytes > ctx->stage_bytes) {
+        if (ctx->stage) SS_CUDA_CHECK(ctx, cudaFreeHost(ctx->stage));
+        ctx->stage = nullptr;
+        ctx->stage_bytes = 0;
+        const size_t want = (bytes + (1u << 20) - 1) & ~(size_t)((1u << 20) - 1);
+        SS_CUDA_CHECK(ctx, cudaHostAlloc(&ctx->stage, want, cudaHostAllocDefault));
+        ctx->stage_bytes = want;
+    }
+    if (!ctx->stage_done) SS_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&ctx->stage_done, cudaEventDisableTiming));
+    memcpy(ctx->stage, h_src, bytes);
+    SS_CUDA_CHECK(ctx, cudaMemcpyAsync(d_dst, ctx->stage, bytes, cudaMemcpyHostToDevice, st));
+    SS_CUDA_CHECK(ctx, cudaEventRecord(ctx->stage_done, st));
+    ctx->stage_busy = true;
+    return SS_OK;
 }
 
 void dev_trim(ss_ctx *ctx) {
@@ -103,6 +125,8 @@ void ss_destroy(ss_ctx *ctx) {
     for (auto &kv : ctx->pool_size) cudaFree(kv.first);       // blocks still held by live trees die with the context
     for (auto &kv : ctx->tables) cudaFree(kv.second);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->stage) cudaFreeHost(ctx->stage);
+    if (ctx->stage_done) cudaEventDestroy(ctx->stage_done);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -29,7 +29,7 @@ enum Kind : uint32_t { K_SLOT, K_CONST, K_TAP, K_TABLE, K_X, K_COUNT };
 constexpr int MAX_SLOTS = 256;
 constexpr int SMALL_SLOTS = 32;
 constexpr uint32_t MAGIC = 0x50435353u;
-constexpr uint32_t VERSION = 2;
+constexpr uint32_t VERSION = 3;
 constexpr int T_XLO = 20, T_XHI = 21;
 
 struct EvalArgs {
@@ -69,13 +69,26 @@ __device__ __forceinline__ Fp fetch(const uint32_t w, const Fp *s, const EvalArg
     }
     case K_TABLE: {
         const uint2 td = __ldg(A.tdesc + pay);
-        return ldg_fp(A.tables + td.y + (i & ((1ull << td.x) - 1)));
+        return ldg_fp(A.tables + td.y + (i & ((1ull << (td.x & 0xffu)) - 1)));
     }
     default: {                                                                   // K_X
         Fp v = ldg_fp(A.xlo + (i & 4095ull));
         if (i >> 12) v = fp::mul(v, ldg_fp(A.xhi + (i >> 12)));
         return v;
     }
+    }
+}
+
+// Tables stored as (challenge-independent values, index of a per-proof constant): multiply them out once, in place,
+// right after the blob is uploaded (program.py: descriptor word 0 = log_period | (scale + 1) << 8).
+__global__ void table_scale_kernel(Fp *tables, const uint2 *tdesc, const Fp *consts, int n_tables) {
+    for (int t = 0; t < n_tables; ++t) {
+        const uint2 td = tdesc[t];
+        if (!(td.x >> 8)) continue;
+        const Fp c = consts[(td.x >> 8) - 1];
+        const unsigned long long T = 1ull << (td.x & 0xffu);
+        for (unsigned long long j = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; j < T; j += (unsigned long long)gridDim.x * blockDim.x)
+            tables[td.y + j] = fp::canon(fp::mul(tables[td.y + j], c));
     }
 }
 
@@ -213,10 +226,12 @@ ss_status ss_constraint_eval(ss_ctx *ctx, const void *h_program, size_t program_
     size_t head_bytes = (head_words * 4 + 31) / 32 * 32;
     if (head_bytes > program_bytes) return fail(ctx, SS_ERR_INVALID, "ss_constraint_eval: blob size mismatch");
     size_t table_elems = 0;
+    bool scaled_tables = false;
     for (uint32_t t = 0; t < n_tables; ++t) {
-        const uint32_t lp = w[16 + 2 * t], off = w[16 + 2 * t + 1];
-        if (lp > 20 || off != table_elems) return fail(ctx, SS_ERR_INVALID, "ss_constraint_eval: corrupt table descriptor %u", t);
+        const uint32_t lp = w[16 + 2 * t] & 0xffu, scale = w[16 + 2 * t] >> 8, off = w[16 + 2 * t + 1];
+        if (lp > 20 || off != table_elems || scale > n_consts) return fail(ctx, SS_ERR_INVALID, "ss_constraint_eval: corrupt table descriptor %u", t);
         table_elems += (size_t)1 << lp;
+        scaled_tables |= scale != 0;
     }
     if (program_bytes != head_bytes + 32 * ((size_t)n_consts + table_elems))
         return fail(ctx, SS_ERR_INVALID, "ss_constraint_eval: blob size mismatch");
@@ -260,17 +275,22 @@ ss_status ss_constraint_eval(ss_ctx *ctx, const void *h_program, size_t program_
         }
         if (!ok) return fail(ctx, SS_ERR_INVALID, "ss_constraint_eval: invalid instruction at word %u (op %u)", pc, op);
     }
+    if (log_row_step < 0 || log_row_step > log_N) return fail(ctx, SS_ERR_INVALID, "ss_constraint_eval: bad row step");
+    const size_t N = (size_t)1 << log_N;
+    if (row_count == 0) { row_begin = 0; row_count = N >> log_row_step; }   // 0 = the whole domain
+    if ((row_begin & ((1ull << log_row_step) - 1)) || row_begin + (row_count << log_row_step) > N)
+        return fail(ctx, SS_ERR_INVALID, "ss_constraint_eval: row range outside the domain");
     SS_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = pick_stream(ctx, stream);
-    // upload the program (stream-ordered; freed after the kernel on the same stream)
-    uint8_t *d_prog = nullptr;
-    SS_CUDA_CHECK(ctx, cudaMallocAsync(reinterpret_cast<void **>(&d_prog), program_bytes, st));
-    SS_CUDA_CHECK(ctx, cudaMemcpyAsync(d_prog, h_program, program_bytes, cudaMemcpyHostToDevice, st));
     Fp *xlo, *xhi;
-    const size_t N = (size_t)1 << log_N;
     ss_status rc;
     if ((rc = cached_table(ctx, {T_XLO, log_N, 0}, N < 4096 ? N : 4096, fill_xlo, &xlo))) return rc;
     if ((rc = cached_table(ctx, {T_XHI, log_N, 0}, N <= 4096 ? 1 : N / 4096, fill_xhi, &xhi))) return rc;
+    // upload the program through the context's pinned staging area: stream-ordered, the caller is not blocked and
+    // may reuse its blob as soon as this returns.  (Everything that can fail has been checked above: no leak paths.)
+    uint8_t *d_prog = nullptr;
+    SS_CUDA_CHECK(ctx, dev_alloc(ctx, reinterpret_cast<void **>(&d_prog), program_bytes));
+    if ((rc = stage_upload(ctx, d_prog, h_program, program_bytes, st))) { dev_free(ctx, d_prog); return rc; }
     EvalArgs A;
     A.tdesc = reinterpret_cast<const uint2 *>(d_prog + 64);
     A.taps = reinterpret_cast<const uint2 *>(d_prog + 64 + 8 * n_tdesc);
@@ -283,10 +303,10 @@ ss_status ss_constraint_eval(ss_ctx *ctx, const void *h_program, size_t program_
     A.log_N = log_N;
     A.xlo = xlo; A.xhi = xhi;
     A.out = static_cast<Fp *>(d_out);
-    if (log_row_step < 0 || log_row_step > log_N) return fail(ctx, SS_ERR_INVALID, "ss_constraint_eval: bad row step");
-    if (row_count == 0) { row_begin = 0; row_count = N >> log_row_step; }   // 0 = the whole domain
-    if ((row_begin & ((1ull << log_row_step) - 1)) || row_begin + (row_count << log_row_step) > N)
-        return fail(ctx, SS_ERR_INVALID, "ss_constraint_eval: row range outside the domain");
+    if (scaled_tables) {
+        table_scale_kernel<<<148, 256, 0, st>>>(const_cast<Fp *>(A.tables), A.tdesc, A.consts, (int)n_tables);
+        ctx->launches++;
+    }
     A.row_begin = row_begin; A.row_count = row_count; A.log_step = log_row_step;
     // tuning switches: ss_set_option, with the environment as the default
     static const int env_minb = [] { const char *e = getenv("SS_CE_MINB"); return e ? atoi(e) : 5; }();
@@ -316,10 +336,9 @@ ss_status ss_constraint_eval(ss_ctx *ctx, const void *h_program, size_t program_
     else
         constraint_eval_kernel<SMALL_SLOTS, 5><<<grid, 128, 0, st>>>(A);
     ctx->launches++;
-    SS_CUDA_CHECK(ctx, cudaGetLastError());
-    SS_CUDA_CHECK(ctx, cudaFreeAsync(d_prog, st));
-    // the host blob may be pageable: make sure the copy has consumed it before returning
-    SS_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    const cudaError_t launch_err = cudaGetLastError();
+    dev_free(ctx, d_prog);                                  // handed out again in stream order (ctx.h)
+    SS_CUDA_CHECK(ctx, launch_err);
     return SS_OK;
 }
 

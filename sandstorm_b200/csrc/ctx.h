@@ -25,6 +25,11 @@ struct ss_ctx {
     // device blocks released by dev_free, kept for reuse (size -> pointers) and the size of every live block
     std::multimap<size_t, void *> pool_free;
     std::map<void *, size_t> pool_size;
+    // pinned staging area for small host -> device uploads that must not block the caller (program blobs)
+    void *stage = nullptr;
+    size_t stage_bytes = 0;
+    cudaEvent_t stage_done = nullptr;
+    bool stage_busy = false;
 };
 
 namespace ss {
@@ -62,6 +67,9 @@ ss_status scratch_reserve(ss_ctx *ctx, size_t bytes, void **out);
 cudaError_t dev_alloc(ss_ctx *ctx, void **out, size_t bytes);
 void dev_free(ss_ctx *ctx, void *ptr);
 void dev_trim(ss_ctx *ctx);
+// Stream-ordered upload of a pageable host buffer without synchronising the stream: the bytes are copied into a
+// pinned staging area owned by the context (waiting only for the PREVIOUS staged upload, if it is still in flight).
+ss_status stage_upload(ss_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, cudaStream_t st);
 // Goldilocks transforms (ntt_goldilocks.cu): one u64 per element, same semantics as the Fp252 entry points
 ss_status gl_ntt(ss_ctx *ctx, void *d_cols, uint64_t col_stride, int n_cols, int log_n, int inverse, int coset, ss_order in_order,
                  ss_order out_order, cudaStream_t st);

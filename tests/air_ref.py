@@ -28,7 +28,7 @@ def eval_expr(e, i, lde_int, log_n, log_blowup, challenges, hints, coeffs, memo=
         elif op == "neg": v = -go(e.args[0]) % P
         else:
             a, b = go(e.args[0]), go(e.args[1])
-            v = {"add": a + b, "sub": a - b, "mul": a * b, "div": a * pow(b, -1, P)}[op] % P
+            v = (a + b if op == "add" else a - b if op == "sub" else a * b if op == "mul" else a * pow(b, -1, P)) % P
         memo[e] = v
         return v
 

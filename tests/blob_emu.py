@@ -36,7 +36,7 @@ def red(v: int) -> int:
 def run_blob(blob, i, lde_int, log_N, stats=None):
     """lde_int[col][row]: canonical field elements.  Returns the canonical output of row i."""
     w = struct.unpack_from("<16I", blob, 0)
-    assert w[0] == 0x50435353 and w[1] == 2
+    assert w[0] == 0x50435353 and w[1] == 3
     n_words, n_consts, n_tables, n_slots, n_taps = w[2], w[3], w[4], w[5], w[8]
     nt = n_tables + (n_tables & 1)
     ntap = n_taps + (n_taps & 1)
@@ -63,7 +63,9 @@ def run_blob(blob, i, lde_int, log_N, stats=None):
             col, off = taps[2 * pay], taps[2 * pay + 1]
             return lde_int[col][(i + off) % N] * R % P
         if kind == K_TABLE:
-            return raw(n_consts + tdesc[2 * pay + 1] + (i & ((1 << tdesc[2 * pay]) - 1)))
+            lp, scale = tdesc[2 * pay] & 0xFF, tdesc[2 * pay] >> 8
+            v = raw(n_consts + tdesc[2 * pay + 1] + (i & ((1 << lp) - 1)))
+            return v * raw(scale - 1) * RINV % P if scale else v          # the device multiplies scaled tables out once
         if kind == K_X:
             return 3 * pow(wN, i, P) * R % P
         raise AssertionError(kind)

@@ -149,9 +149,65 @@ def test_generated_kernel_registry_matches_prover_programs(name, log_n):
     L = load_layout(name)
     C, ce, n = L.num_columns, 2, 1 << log_n
     rnd = random.Random(991 + log_n)
-    comp = compile_program(L.composition(n, inv_x_minus_one_col=C + ce), log_n, 1, [rnd.randrange(P) for _ in range(L.n_challenges())],
-                           [rnd.randrange(P) for _ in range(L.n_hints())], [rnd.randrange(P)], with_tables=False)
+    from sandstorm_b200.air import compile_template
+
+    # (the prover compiles the composition as a template and patches the challenges in; hints of a real proof are 0 / 1 / small)
+    comp = compile_template(L.composition(n, inv_x_minus_one_col=C + ce), log_n, 1, L.n_challenges(), L.n_hints(), 1, with_tables=False)
+    comp = comp.patch([rnd.randrange(P) for _ in range(L.n_challenges())], [rnd.randrange(3) for _ in range(L.n_hints())], [rnd.randrange(P)])
     tt, ct = deep_terms(L.taps(), [rnd.randrange(P) for _ in L.taps()], [rnd.randrange(P) for _ in range(ce)], C, rnd.randrange(P), P)
     deep = compile_program(deep_expr_shifted(tt, ct, C + ce + 1, C + ce + 2, pow(3, (P - 1) // n, P), P), log_n, 1, with_tables=False)
     assert registry.get(structure_hash(comp.blob), "").startswith(f"{name}_composition")
     assert registry.get(structure_hash(deep.blob), "").startswith(f"{name}_deep")
+
+
+@pytest.mark.parametrize("special_hints", [False, True])
+def test_template_patch_equals_direct_evaluation(special_hints):
+    """compile_template (tracked challenges, air/symbolic.py) + patch(values): the patched program evaluates the
+    expression for those values — for generic draws and for hints that are 0 / 1 (which a direct compilation would
+    fold into a different structure) — and its structure does not depend on the values."""
+    from sandstorm_b200.air import compile_template
+    from sandstorm_b200.air.program import structure_hash
+
+    rng = np.random.default_rng(77)
+    log_n, log_blowup = 4, 1
+    n, N = 1 << log_n, 1 << (log_n + log_blowup)
+    lde_int = [[int.from_bytes(rng.bytes(31), "big") for _ in range(N)] for _ in range(3)]
+    expr = composition_constraint(toy_air(n))
+    tpl = compile_template(expr, log_n, log_blowup, n_challenges=2, n_hints=2, n_coeffs=1)
+    hashes = set()
+    for draw in range(2):
+        challenges = [int.from_bytes(rng.bytes(31), "big") for _ in range(2)]
+        hints = [draw, 1 - draw] if special_hints else [int.from_bytes(rng.bytes(31), "big") for _ in range(2)]
+        alpha = [int.from_bytes(rng.bytes(31), "big")]
+        prog = tpl.patch(challenges, hints, alpha)
+        hashes.add(structure_hash(prog.blob))
+        for i in list(range(8)) + [N - 1, N // 2 + 1]:
+            assert run_blob(prog.blob, i, lde_int, log_n + log_blowup) == eval_expr(expr, i, lde_int, log_n, log_blowup, challenges, hints, alpha), i
+    assert len(hashes) == 1
+    with pytest.raises(ValueError):
+        tpl.patch([1], [2, 3], [4])
+
+
+def test_template_of_a_real_layout_matches_tree_evaluator():
+    """recursive layout at its minimum trace length: template + patch through the device emulator == the big-int tree
+    evaluator of the same constraints (challenge-dependent table factors are multiplied out the way the device does)."""
+    import random
+
+    from sandstorm_b200.air import compile_template
+    from sandstorm_b200.air.layouts import load_layout
+
+    L = load_layout("recursive")
+    log_n, b = 11, 1
+    n, N = 1 << log_n, 1 << (log_n + b)
+    rnd = random.Random(5)
+    C = L.num_columns
+    lde = [[rnd.randrange(P) for _ in range(N)] for _ in range(C)]
+    w = pow(3, (P - 1) // N, P)
+    w_col = [pow(3 * pow(w, i, P) - 1, -1, P) for i in range(N)]
+    tpl = compile_template(L.composition(n, inv_x_minus_one_col=C), log_n, b, L.n_challenges(), L.n_hints(), 1)
+    ch, hints, alpha = [rnd.randrange(P) for _ in range(L.n_challenges())], [rnd.randrange(P) for _ in range(L.n_hints())], [rnd.randrange(P)]
+    hints[5], hints[8], hints[9] = 1, 1, 0                       # RangeCheckProduct, DilutedCheckProduct, DilutedCheckFirst of a real proof
+    prog = tpl.patch(ch, hints, alpha)
+    expr = L.composition(n)
+    for i in (0, 1, 5, 2047, N - 3):
+        assert run_blob(prog.blob, i, lde + [w_col], log_n + b) == eval_expr(expr, i, lde, log_n, b, ch, hints, alpha), i

@@ -24,7 +24,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from sandstorm_b200.air import compile_program  # noqa: E402
+from sandstorm_b200.air import compile_program, compile_template  # noqa: E402
 from sandstorm_b200.air.deep import deep_expr_shifted, deep_terms  # noqa: E402
 from sandstorm_b200.air.expr import P  # noqa: E402
 from sandstorm_b200.air.layouts import load_layout  # noqa: E402
@@ -53,7 +53,7 @@ def operand(word: int, d: dict) -> str:
     if kind == K_TAP:
         return f"ldg_fp(A.cols + {d['taps'][2 * pay]}ull * A.stride + ((i + G.tap_off[{pay}]) & mask))"
     if kind == K_TABLE:
-        return f"ldg_fp(A.tables + G.tab_off[{pay}] + (i & {(1 << d['tdesc'][2 * pay]) - 1}ull))"
+        return f"ldg_fp(A.tables + G.tab_off[{pay}] + (i & {(1 << (d['tdesc'][2 * pay] & 0xFF)) - 1}ull))"
     if kind == K_X:
         return "fetch_x(A, i)"
     raise ValueError(kind)
@@ -111,8 +111,8 @@ def programs():
         C, n = L.num_columns, 1 << log_n
         ce = 2
         w_col = C + ce                                         # HotPathProver column map: trace | composition | w | u | v
-        comp = compile_program(L.composition(n, inv_x_minus_one_col=w_col), log_n, 1, [rnd.randrange(P) for _ in range(L.n_challenges())],
-                               [rnd.randrange(P) for _ in range(L.n_hints())], [rnd.randrange(P)], with_tables=False)
+        comp = compile_template(L.composition(n, inv_x_minus_one_col=w_col), log_n, 1, L.n_challenges(), L.n_hints(), 1, with_tables=False)
+        comp = comp.patch([rnd.randrange(P) for _ in range(L.n_challenges())], [rnd.randrange(P) for _ in range(L.n_hints())], [rnd.randrange(P)])
         out.append((f"{layout}_composition", comp.blob, 3))
         g = pow(3, (P - 1) // n, P)
         tt, ct = deep_terms(L.taps(), [rnd.randrange(P) for _ in L.taps()], [rnd.randrange(P) for _ in range(ce)], C, rnd.randrange(P), P)
