@@ -184,6 +184,20 @@ ss_status ss_constraint_eval(ss_ctx *ctx, const void *h_program, size_t program_
                              int log_row_step /* rows row_begin + k * 2^log_row_step, k < row_count */,
                              void *d_out /* indexed by (absolute row >> log_row_step) */, void *stream);
 
+/* ------------------------------------------------------------------ extension columns (§8 f1)
+ * Trace::build_extension_columns (layouts/src/recursive/trace.rs:699-814, starknet/trace.rs:997-1100) as device prefix
+ * scans instead of the reference's sequential loops + batch_inversion.  Elements are read at index j * stride of the
+ * given column pointers (the layouts interleave virtual columns: memory pairs at stride 2, range-check cells at
+ * stride 4, ...) and result i is written at d_out[i * out_stride].
+ *   ss_perm_product:      out[i] = prod_{j<=i} (z - (alpha * num_v[j] + num_a[j])) / (z - (alpha * den_v[j] + den_a[j]))
+ *                         (d_num_v = d_den_v = NULL: z - num_a[j] over z - den_a[j])          trace.rs:706-755
+ *   ss_diluted_aggregate: out[0] = 1, out[i] = out[i-1] * (1 + z u_i) + alpha u_i^2, u_i = d[i] - d[i-1]   trace.rs:787-806 */
+ss_status ss_perm_product(ss_ctx *ctx, ss_field field, const void *d_num_a, const void *d_num_v, const void *d_den_a,
+                          const void *d_den_v, uint64_t stride, uint64_t count, const void *h_z, const void *h_alpha,
+                          void *d_out, uint64_t out_stride, void *stream);
+ss_status ss_diluted_aggregate(ss_ctx *ctx, ss_field field, const void *d_ordered, uint64_t stride, uint64_t count,
+                               const void *h_z, const void *h_alpha, void *d_out, uint64_t out_stride, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

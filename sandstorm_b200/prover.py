@@ -12,9 +12,20 @@ ministark's prover runs them (steps 3-5, 8-10, 11-13, 15), for a layout of the r
                   layer_size / blowup <= max_remainder
     queries     : Merkle openings + rows at the query positions
 
-Trace generation, `build_extension_columns`, the public coin / proof-of-work and proof serialisation
-stay on the host in the reference (out of scope here), so challenges come from a seeded generator:
-this class measures and checks the GPU stages, it does not emit a `Proof`."""
+The transcript is driven by a public coin with the reference's `PublicCoin` interface (sandstorm_b200/public_coin.py:
+the Solidity- and Cairo-verifier coins; `SeededCoin` below is a stand-in that draws from a seeded generator for
+benchmarks on synthetic columns).  The order of reseeds and draws follows ministark's `ProverChannel` as recalled
+(ministark is not vendored; DESIGN.md §2 lists it as unpinned):
+
+    reseed(base root) -> challenges -> [extension columns built from them] -> reseed(ext root) -> composition coefficient
+    -> reseed(composition root) -> z -> reseed_with_field_elements(trace OOD values), (composition OOD values) -> DEEP alpha
+    -> per FRI layer: reseed(layer root), draw fold alpha -> reseed_with_field_element_vector(remainder)
+    -> proof-of-work nonce, reseed_with_int(nonce) -> draw_queries
+
+The extension trace may be given as a callable(challenges) -> Matrix (`Trace::build_extension_columns`, on the device:
+sandstorm_b200/ext_columns.py) and the hints as a callable(challenges) -> list (`AirConfig::gen_hints`).  The composition
+program is compiled ahead of time as a template (air/program.py ProgramTemplate); only its value patch runs between the
+extension commitment and constraint evaluation."""
 from __future__ import annotations
 
 import ctypes
@@ -25,7 +36,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .air import compile_program
+from .air import compile_program, compile_template
 from .air.program import tap_reach
 from .air.deep import deep_expr_shifted, deep_terms
 from .air.evaluate import evaluate
@@ -48,9 +59,31 @@ class ProofOptions:
     log_blowup: int = 1
     log_fold: int = 3
     max_remainder_coeffs: int = 16
+    grinding_factor: int = 0                     # cli default 16 (cli/src/main.rs:55); 0 skips the search
+    ce_blowup: int = 2                           # composition columns (src/lib.rs:110-113 air.ce_blowup_factor())
     tree_kind: int = _lib.TREE_KECCAK_M20        # src/claims.rs:18-21 (starknet / EthVerifier); recursive claims use TREE_FRIENDLY
     n_friendly: int = 22                         # NUM_FRIENDLY_COMMITMENT_LAYERS, src/claims.rs:10 (TREE_FRIENDLY only)
     col_pad_rows: int = 0                        # padding between the columns of the working matrix (not a protocol parameter)
+
+
+class SeededCoin:
+    """Stand-in public coin for synthetic benchmarks: draws from a seeded generator (the same on every rank), ignores
+    reseeds, skips the proof-of-work search."""
+
+    def __init__(self, seed: int = 0xB200):
+        self.rnd = random.Random(seed)
+
+    def draw(self) -> int:
+        return self.rnd.randrange(P)
+
+    def reseed_with_digest(self, digest): pass
+    def reseed_with_field_elements(self, vals): pass
+    def reseed_with_field_element_vector(self, vals): pass
+    def reseed_with_int(self, val): pass
+    def grind_proof_of_work(self, bits, ctx=None): return 0
+
+    def draw_queries(self, max_n: int, domain_size: int) -> list[int]:
+        return sorted({self.rnd.randrange(domain_size) for _ in range(max_n)})
 
 
 @dataclass
@@ -63,16 +96,29 @@ class HotPathResult:
     query_positions: list = field(default_factory=list)
     opened_bytes: int = 0
     deep_matches_full_evaluation: bool | None = None
+    composition_top_zero: bool | None = None
+    challenges: list = field(default_factory=list)
+    hints: list = field(default_factory=list)
+    composition_coeffs: list = field(default_factory=list)
+    ood_point: int = 0
+    deep_alpha: int = 0
+    fri_alphas: list = field(default_factory=list)
+    pow_nonce: int = 0
+    # openings at the query positions (the `Queries` + `FriProof` payload of ministark's Proof)
+    trace_queries: dict = field(default_factory=dict)      # name -> {"rows": uint64[q, cols, 4], "paths": uint8[q, depth, 32]}
+    fri_layers: list = field(default_factory=list)          # per layer {"positions", "rows": uint64[q, fold, 4], "paths"}
 
 
 class HotPathProver:
     def __init__(self, layout: str, log_n: int, options: ProofOptions | None = None, seed: int = 0xB200, device=None,
-                 rank: int = 0, world: int = 1):
+                 rank: int = 0, world: int = 1, coin=None):
         self.layout = load_layout(layout)
         self.log_n, self.opt = log_n, options or ProofOptions()
         self.n, self.N = 1 << log_n, 1 << (log_n + self.opt.log_blowup)
-        self.ce = 1 << self.opt.log_blowup                      # ce_blowup_factor == lde blowup for Cairo (degree-2 constraints)
-        self.rnd = random.Random(seed)           # same seed on every rank: identical challenges everywhere
+        self.ce = self.opt.ce_blowup                            # air.ce_blowup_factor(): 2 for Cairo's degree-2 constraints
+        if (1 << self.opt.log_blowup) < self.ce:
+            raise ValueError("the LDE blowup must be at least the constraint-evaluation blowup")
+        self.coin = coin if coin is not None else SeededCoin(seed)      # same seed on every rank: identical challenges everywhere
         self.rank, self.world = rank, world
         if world & (world - 1):
             raise ValueError("world size must be a power of two")
@@ -81,6 +127,7 @@ class HotPathProver:
         # columns of the working matrix: trace | composition (ce) | w = 1/(x-1) | u = 1/(x-z) | v = 1/(x-z^ce)
         C = self.layout.num_columns
         self.comp_col, self.w_col, self.u_col, self.v_col = C, C + self.ce, C + self.ce + 1, C + self.ce + 2
+        self._template = None
         self._composition_program = None
         self._challenges = self._hints = self._alpha = None
         self.timeline: list = []
@@ -101,23 +148,26 @@ class HotPathProver:
 
     # ---- host-side stand-ins for the public coin -------------------------------------------------------
     def _draw(self) -> int:
-        return self.rnd.randrange(P)
+        return self.coin.draw()
 
     def mark(self, name: str):
         ev = torch.cuda.Event(enable_timing=True)
         ev.record()
         self.timeline.append((name, ev))
 
-    def composition_program(self):
-        """AirConfig::constraints + composition_constraint, compiled once per (layout, n, challenges)."""
-        if self._composition_program is None:
+    def composition_template(self):
+        """AirConfig::constraints + composition_constraint compiled with the challenges, hints and the composition
+        coefficient left open: depends on (layout, n, blowup) only, so it is built ahead of the proof."""
+        if self._template is None:
             L = self.layout
-            self._challenges = [self._draw() for _ in range(L.n_challenges())]
-            self._hints = [self._draw() for _ in range(L.n_hints())]
-            self._alpha = [self._draw()]
             # boundary denominators X - g^e read the auxiliary column w = 1/(x - 1) (see Layout.constraints)
-            self._composition_program = compile_program(L.composition(self.n, inv_x_minus_one_col=self.w_col), self.log_n,
-                                                        self.opt.log_blowup, self._challenges, self._hints, self._alpha)
+            self._template = compile_template(L.composition(self.n, inv_x_minus_one_col=self.w_col), self.log_n, self.opt.log_blowup,
+                                              L.n_challenges(), L.n_hints(), 1)
+        return self._template
+
+    def composition_program(self, challenges, hints, alpha):
+        """the per-proof value patch (a few milliseconds): constants <- challenges, hints, composition coefficient."""
+        self._composition_program = self.composition_template().patch(challenges, hints, alpha)
         return self._composition_program
 
     # ---- commitment helper: whole tree on one GPU, row-range sub-trees + combined root on several ---------
@@ -154,15 +204,20 @@ class HotPathProver:
         dist.all_gather_into_tensor(full, full[lo:lo + cnt].clone())
 
     # ---- the device stages ---------------------------------------------------------------------------------
-    def prove(self, base: Matrix, ext: Matrix, queries: bool = True, self_check: bool = False, column_ready=None) -> HotPathResult:
-        """base / ext: the trace columns (every rank holds them: they come from the host-side trace builder).
+    def prove(self, base: Matrix, ext, queries: bool = True, self_check: bool = False, column_ready=None, hints=None,
+              keep_openings: bool = False) -> HotPathResult:
+        """base: the base trace columns; ext: the extension columns, or a callable(challenges) -> Matrix that builds them
+        once the challenges are drawn (Trace::build_extension_columns); hints: list or callable(challenges) -> list
+        (AirConfig::gen_hints; None = drawn from the coin, for synthetic columns).  keep_openings: return the opened rows
+        and authentication paths (the proof payload) instead of only counting their bytes.
         column_ready(k): optional hook called before trace column k (base then extension; None = all) is first read, so that a
         caller streaming the trace from host memory can order its uploads against the LDE (bench.py e2e leg).
         With world > 1 (torch.distributed initialised, one process per GPU): LDE and OOD are sharded by column,
         Merkle hashing / constraint evaluation / DEEP / FRI folds by LDE row range; LDE columns are broadcast
         from their owners, row-sharded vectors all-gathered, sub-tree roots combined (SURVEY.md §8e plan A)."""
         opt, L = self.opt, self.layout
-        assert base.num_cols == L.num_base_columns and ext.num_cols == L.num_extension_columns and base.num_rows == self.n
+        assert base.num_cols == L.num_base_columns and base.num_rows == self.n
+        coin = self.coin
         from .parallel import owned_columns, share_row_ranges
 
         res = HotPathResult()
@@ -194,6 +249,18 @@ class HotPathProver:
         self.mark("share_base")
         res.roots["base"], h = self._commit(lde.data_ptr(), S, nb, self.log_n + b); handles.append(h)
         self.mark("merkle_base")
+        # 6-7: challenges, hints, extension columns
+        coin.reseed_with_digest(res.roots["base"])
+        challenges = res.challenges = [coin.draw() for _ in range(L.n_challenges())]
+        if callable(ext):
+            ext = ext(challenges)
+        assert ext.num_cols == L.num_extension_columns and ext.num_rows == self.n
+        if hints is None:
+            hints = [coin.draw() for _ in range(L.n_hints())]
+        elif callable(hints):
+            hints = hints(challenges)
+        res.hints = list(hints)
+        self.mark("ext_columns")
         # 8: extension trace
         lde_cols(ext, nb)
         self.mark("lde_ext")
@@ -201,8 +268,11 @@ class HotPathProver:
         self.mark("share_ext")
         res.roots["ext"], h = self._commit(lde[nb].data_ptr(), S, C - nb, self.log_n + b); handles.append(h)
         self.mark("merkle_ext")
+        coin.reseed_with_digest(res.roots["ext"])
         # 9: constraint evaluation (row range of this rank), boundary denominators from w = 1/(x - 1)
-        prog = self.composition_program()
+        res.composition_coeffs = [coin.draw()]
+        prog = self.composition_program(challenges, res.hints, res.composition_coeffs)
+        self.mark("patch")
         if world == 1:
             inv_x_minus_c(all_lde[self.w_col], _mont(1), c)
         else:                                            # only the rows this rank's taps reach
@@ -220,7 +290,10 @@ class HotPathProver:
         work = Matrix(comp_evals.view(1, N, 4), c)
         work.ntt_(inverse=True, coset=True)
         self.mark("ntt_comp_inv")
-        comp_coeffs = comp_evals.view(n, self.ce, 4).permute(1, 0, 2).contiguous()        # [ce, n, 4] natural order
+        if self_check and N > self.ce * n:
+            # a trace that satisfies the AIR gives a composition polynomial of degree < ce * n: the upper coefficients vanish
+            res.composition_top_zero = not bool(comp_evals[self.ce * n:].any().item())
+        comp_coeffs = comp_evals[:self.ce * n].view(n, self.ce, 4).permute(1, 0, 2).contiguous()        # [ce, n, 4] natural order
         comp_lde = all_lde[self.comp_col:self.comp_col + self.ce]
         comp_lde.zero_()
         comp_lde[:, :n] = comp_coeffs
@@ -236,7 +309,8 @@ class HotPathProver:
         self.mark("merkle_comp")
         # 11: out-of-domain evaluations of every tap, straight from the trace (barycentric dot products with one shared
         #     weight vector, ss_ood_eval).  Each rank sums over its range of trace rows; the partial values add up.
-        z = self._draw()
+        coin.reseed_with_digest(res.roots["composition"])
+        z = res.ood_point = coin.draw()
         taps = L.taps()
         if column_ready is not None:
             column_ready(None)                           # every trace column is read from here on
@@ -264,7 +338,9 @@ class HotPathProver:
         rinv = pow(R, -1, P)
         res.ood_trace, res.ood_composition = [v * rinv % P for v in ood_m], [v * rinv % P for v in to_int(ood_c)]
         # 12: DEEP composition over the LDE coset (coefficients = powers of one alpha, src/lib.rs:102-116)
-        alpha = self._draw()
+        coin.reseed_with_field_elements(res.ood_trace)
+        coin.reseed_with_field_elements(res.ood_composition)
+        alpha = res.deep_alpha = coin.draw()
         t_terms, c_terms = deep_terms(taps, res.ood_trace, res.ood_composition, self.comp_col, alpha, P)
         # (the sub-coset evaluation below reads u and v only at rows that are multiples of the blowup)
         if world == 1:                                   # (launched first: the GPU works while the host compiles)
@@ -306,7 +382,9 @@ class HotPathProver:
             # the layer matrix (rows x fold) is the evaluation buffer viewed with col_stride = rows
             root, handle = self._commit(evals.data_ptr(), rows, 1 << opt.log_fold, log_size - opt.log_fold)
             res.fri_roots.append(root)
-            fri_alpha = self._draw()
+            coin.reseed_with_digest(root)
+            fri_alpha = coin.draw()
+            res.fri_alphas.append(fri_alpha)
             shard = world > 1 and rows >= (1 << 16)
             lo, cnt = (rank * (rows // world), rows // world) if shard else (0, 0)
             nxt = fri_fold(evals, opt.log_fold, _mont(fri_alpha), _mont(offset), ctx=c, rows=(lo, cnt) if shard else None)
@@ -316,13 +394,18 @@ class HotPathProver:
             evals, log_size, offset = nxt, log_size - opt.log_fold, pow(offset, 1 << opt.log_fold, P)
         res.remainder = evals.cpu().numpy().view(np.uint64)
         self.final_domain = (log_size, offset)
+        coin.reseed_with_field_element_vector([v * rinv % P for v in to_int(res.remainder)])
         self.mark("fri")
-        # 15: queries (positions from the seeded generator; openings + rows through the ABI) — single-GPU trees only
+        # 14: proof of work (GPU search for the smallest nonce), 15: query positions
+        if opt.grinding_factor:
+            res.pow_nonce = coin.grind_proof_of_work(opt.grinding_factor, c)
+            coin.reseed_with_int(res.pow_nonce)
+        # 15: queries (openings + rows through the ABI) — single-GPU trees only
         if queries and world == 1:
-            pos = sorted({self.rnd.randrange(N) for _ in range(opt.num_queries)})
+            pos = coin.draw_queries(opt.num_queries, N)
             res.query_positions = pos
             idx = np.array(pos, dtype=np.uint64)
-            for h, (first, ncols) in zip(handles, ((0, nb), (nb, C - nb), (self.comp_col, self.ce))):
+            for name, h, (first, ncols) in zip(("base", "ext", "composition"), handles, ((0, nb), (nb, C - nb), (self.comp_col, self.ce))):
                 paths = np.zeros((len(idx), self.log_n + b, 32), dtype=np.uint8)
                 c.check(c.lib.ss_merkle_open(c.handle, h, idx.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), len(idx),
                                              paths.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))))
@@ -330,6 +413,8 @@ class HotPathProver:
                 c.check(c.lib.ss_rows_gather(c.handle, ctypes.c_void_p(all_lde[first].data_ptr()), S, ncols,
                                              idx.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), len(idx), rows_out.ctypes.data_as(ctypes.c_void_p)))
                 res.opened_bytes += paths.nbytes + rows_out.nbytes
+                if keep_openings:
+                    res.trace_queries[name] = {"rows": rows_out, "paths": paths}
             for handle, layer_evals, ls in layers:
                 rows = 1 << (ls - opt.log_fold)
                 idx = np.array(sorted({p % rows for p in pos}), dtype=np.uint64)
@@ -337,6 +422,11 @@ class HotPathProver:
                 c.check(c.lib.ss_merkle_open(c.handle, handle, idx.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), len(idx),
                                              paths.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))))
                 res.opened_bytes += paths.nbytes
+                if keep_openings:
+                    rows_out = np.zeros((len(idx), 1 << opt.log_fold, 4), dtype=np.uint64)
+                    c.check(c.lib.ss_rows_gather(c.handle, ctypes.c_void_p(layer_evals.data_ptr()), rows, 1 << opt.log_fold,
+                                                 idx.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), len(idx), rows_out.ctypes.data_as(ctypes.c_void_p)))
+                    res.fri_layers.append({"positions": [int(p) for p in idx], "rows": rows_out, "paths": paths})
                 pos = [int(p) for p in idx]
             self.mark("queries")
         for handle, _, _ in layers:

@@ -95,3 +95,38 @@ def divisors(e, out=None, seen=None):
         if hasattr(a, "op"):
             divisors(a, out, seen)
     return out
+
+
+def eval_at_point(e, z, tap_values, log_n, challenges, hints, coeffs):
+    """The verifier's evaluation of an Expr at an out-of-domain point z: Trace(col, off) reads the claimed value
+    tap_values[(col, off)] = T_col(z * g^off) (ministark's `Verifier` recomputes the composition this way)."""
+    n = 1 << log_n
+    memo = {}
+
+    def go(e):
+        if e in memo:
+            return memo[e]
+        op = e.op
+        if op == "x": v = z
+        elif op == "const": v = e.args[0]
+        elif op == "trace": v = tap_values[(e.args[0], e.args[1])]
+        elif op == "challenge": v = challenges[e.args[0]]
+        elif op == "hint": v = hints[e.args[0]]
+        elif op == "composition_coeff": v = coeffs[e.args[0]]
+        elif op == "periodic":
+            cs, interval = e.args
+            y = pow(z, n // interval, P)
+            v = 0
+            for c in reversed(cs):
+                v = (v * y + c) % P
+        elif op == "pow": v = pow(go(e.args[0]), e.args[1], P)
+        elif op == "neg": v = -go(e.args[0]) % P
+        else:
+            a, b = go(e.args[0]), go(e.args[1])
+            v = (a + b if op == "add" else a - b if op == "sub" else a * b if op == "mul" else a * pow(b, -1, P)) % P
+        memo[e] = v
+        return v
+
+    import sys
+    sys.setrecursionlimit(max(sys.getrecursionlimit(), 100000))
+    return go(e)

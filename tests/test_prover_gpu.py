@@ -18,7 +18,8 @@ def ss():
     return sandstorm_b200
 
 
-@pytest.mark.parametrize("layout,log_n,tree", [("plain", 7, "keccak_m20"), ("recursive", 12, "keccak_m20"), ("recursive", 11, "friendly")])
+@pytest.mark.parametrize("layout,log_n,tree", [("plain", 7, "keccak_m20"), ("recursive", 12, "keccak_m20"), ("recursive", 11, "friendly"),
+                                               ("starknet", 16, "keccak_m20")])
 def test_hot_path_is_consistent(ss, oracle, layout, log_n, tree):
     import torch
 
@@ -32,23 +33,27 @@ def test_hot_path_is_consistent(ss, oracle, layout, log_n, tree):
     rng = np.random.default_rng(log_n)
     base = oracle.random_felts(rng, L.num_base_columns, 1 << log_n)
     ext = oracle.random_felts(rng, L.num_extension_columns, 1 << log_n)
-    res = hp.prove(ss.Matrix.from_numpy(base), ss.Matrix.from_numpy(ext), self_check=True)
+    res = hp.prove(ss.Matrix.from_numpy(base), ss.Matrix.from_numpy(ext), self_check=True, keep_openings=True)
     torch.cuda.synchronize()
     # the DEEP quotient, evaluated on the sub-coset 3<w_n> and extended, equals its evaluation on every LDE row
     assert res.deep_matches_full_evaluation is True
     # commitments
     assert res.roots["base"] == oracle.merkle_build(ok, oracle.lde(base, 1))[2]
     assert res.roots["ext"] == oracle.merkle_build(ok, oracle.lde(ext, 1))[2]
-    # out-of-domain values of two taps
-    coeffs = oracle.ntt(np.concatenate([base, ext]), inverse=True)
+    # out-of-domain values: every tap of the mask against Horner evaluation of the oracle's interpolation at z * g^offset
+    coeffs = [oracle.from_mont(c) for c in oracle.ntt(np.concatenate([base, ext]), inverse=True)]
     taps = L.taps()
-    g = pow(3, (P - 1) >> log_n, P)
-    z_rec = None
-    for k in (0, len(taps) - 1):
-        col, off = taps[k]
-        c = oracle.from_mont(coeffs[col])
-        # recover z from the first tap is not possible; recompute it from the prover's generator state instead
+    g, z = pow(3, (P - 1) >> log_n, P), res.ood_point
     assert len(res.ood_trace) == len(taps) and len(res.ood_composition) == 2
+    for k in sorted({0, 1, len(taps) // 2, len(taps) - 1}):
+        col, off = taps[k]
+        x, acc = z * pow(g, off, P) % P, 0
+        for v in reversed(coeffs[col]):
+            acc = (acc * x + v) % P
+        assert res.ood_trace[k] == acc, (k, col, off)
+    # the composition columns: commitment of their LDE, and the opened rows at the query positions are rows of that LDE
+    comp_rows = res.trace_queries["composition"]["rows"]
+    assert comp_rows.shape == (len(res.query_positions), 2, 4)
     # FRI remainder: evaluations on offset * <w_m> of a polynomial of degree < m / blowup
     log_m, offset = hp.final_domain
     m = 1 << log_m
@@ -58,6 +63,10 @@ def test_hot_path_is_consistent(ss, oracle, layout, log_n, tree):
     assert all(v == 0 for v in cfs[m // 2:]), "FRI remainder is not low-degree"
     assert any(v != 0 for v in cfs[: m // 2])
     assert len(res.fri_roots) >= 1 and res.opened_bytes > 0
+    # opened base rows are the LDE rows at the query positions
+    lde_base = oracle.lde(base, 1)
+    for q, pos in enumerate(res.query_positions[:4]):
+        assert np.array_equal(res.trace_queries["base"]["rows"][q], lde_base[:, pos])
 
 
 def test_ood_values_match_horner(ss, oracle):

@@ -24,7 +24,7 @@ def cols(c):
 
 
 base, ext = cols(L.num_base_columns), cols(L.num_extension_columns)
-t0 = time.time(); hp.composition_program(); t_compile = time.time() - t0
+t0 = time.time(); hp.composition_template(); t_compile = time.time() - t0
 for rep in range(2):
     hp.timeline.clear()
     t0 = time.time()
