@@ -184,6 +184,20 @@ ss_status ss_constraint_eval(ss_ctx *ctx, const void *h_program, size_t program_
                              int log_row_step /* rows row_begin + k * 2^log_row_step, k < row_count */,
                              void *d_out /* indexed by (absolute row >> log_row_step) */, void *stream);
 
+/* ------------------------------------------------------------------ row-sharded transforms over W GPUs (§8e plan B)
+ * A transform of size M over W ranks = one all-to-all between a size-W transform across the ranks (ss_shard_dft) and
+ * local size-M/W transforms (ss_ntt_shard); sandstorm_b200/parallel.py drives them with torch.distributed / NCCL.
+ * ss_ntt_shard: stages & 1 = inverse DIF of size 2^log_m (natural -> bit-reversed), coefficient k scaled by c0 * h0^k;
+ *               stages & 2 = forward DIT of size 2^(log_m + log_expand) from bit-reversed coefficients (zero-padded),
+ *               natural output k scaled by tw^k (h_tw NULL: none).  stages = 3: both (the local LDE).
+ * ss_shard_dft: out[k1 * out_stride + i] = tw(i)^k1 * sum_{j1<W} in[j1 * in_stride + i] * w_W^(+-j1 k1), i < count,
+ *               tw(i) = w_(2^tw_log_m)^(+-(tw_offset + i)) (tw_log_m < 0: none); W = 2^log_w <= 8. */
+ss_status ss_ntt_shard(ss_ctx *ctx, ss_field field, const void *d_src, uint64_t src_stride, int n_cols, int log_m, int stages,
+                       int log_expand, const void *h_c0, const void *h_h0, const void *h_tw, void *d_dst, uint64_t dst_stride,
+                       void *stream);
+ss_status ss_shard_dft(ss_ctx *ctx, ss_field field, const void *d_in, uint64_t in_stride, void *d_out, uint64_t out_stride,
+                       uint64_t count, int log_w, int inverse, int tw_log_m, uint64_t tw_offset, void *stream);
+
 /* ------------------------------------------------------------------ extension columns (§8 f1)
  * Trace::build_extension_columns (layouts/src/recursive/trace.rs:699-814, starknet/trace.rs:997-1100) as device prefix
  * scans instead of the reference's sequential loops + batch_inversion.  Elements are read at index j * stride of the

@@ -107,6 +107,53 @@ def ntt(cols: np.ndarray, inverse: bool = False) -> np.ndarray:
     return a
 
 
+def coset_ntt(col: np.ndarray, inverse: bool = False) -> np.ndarray:
+    """one column uint64[n, 4]: ark-poly coset_fft / coset_ifft with offset 3."""
+    a = np.array(col, dtype=np.uint64, order="C", copy=True)
+    lib().oracle_coset_ntt_fp252(_ptr(a), ctypes.c_int(a.shape[0].bit_length() - 1), ctypes.c_int(int(inverse)))
+    return a
+
+
+def constraint_eval(blob: bytes, cols: np.ndarray, log_N: int, out: np.ndarray | None = None, rows=None, log_step: int = 0) -> np.ndarray:
+    """cols: uint64[n_cols, N, 4] (column-major LDE matrix).  Evaluates a program blob (sandstorm_b200/air/program.py) on the
+    rows begin + (k << log_step), k < count; result k is stored at out[row >> log_step]."""
+    a = np.ascontiguousarray(cols, dtype=np.uint64)
+    N = 1 << log_N
+    assert a.shape[1] == N
+    if out is None:
+        out = np.zeros((N >> log_step, 4), dtype=np.uint64)
+    begin, count = rows if rows is not None else (0, 0)
+    rc = lib().oracle_constraint_eval(blob, ctypes.c_size_t(len(blob)), _ptr(a), ctypes.c_uint64(N), ctypes.c_int(log_N),
+                                      ctypes.c_uint64(begin), ctypes.c_uint64(count), ctypes.c_int(log_step), _ptr(out))
+    if rc:
+        raise ValueError(f"oracle_constraint_eval: bad program blob ({rc})")
+    return out
+
+
+def inv_x_minus_c(log_N: int, c: int, log_step: int = 0, out: np.ndarray | None = None) -> np.ndarray:
+    """out[i] = 1 / (3 w_N^i - c) on the rows that are multiples of 2^log_step (c: canonical int)."""
+    if out is None:
+        out = np.zeros((1 << log_N, 4), dtype=np.uint64)
+    lib().oracle_inv_x_minus_c(ctypes.c_int(log_N), ctypes.c_int(log_step), _ptr(to_mont([c])), _ptr(out))
+    return out
+
+
+def horner(coeffs: np.ndarray, z: int) -> int:
+    """P(z) for natural-order Montgomery coefficients uint64[n, 4]; canonical int."""
+    a = np.ascontiguousarray(coeffs, dtype=np.uint64)
+    r = np.zeros((1, 4), dtype=np.uint64)
+    lib().oracle_horner(_ptr(a), ctypes.c_uint64(a.shape[0]), _ptr(to_mont([z])), _ptr(r))
+    return from_mont(r)[0]
+
+
+def fri_fold(evals: np.ndarray, log_fold: int, alpha: int, offset: int) -> np.ndarray:
+    a = np.ascontiguousarray(evals, dtype=np.uint64)
+    log_n = a.shape[0].bit_length() - 1
+    out = np.zeros((a.shape[0] >> log_fold, 4), dtype=np.uint64)
+    lib().oracle_fri_fold(_ptr(a), ctypes.c_int(log_n), ctypes.c_int(log_fold), _ptr(to_mont([alpha])), _ptr(to_mont([offset])), _ptr(out))
+    return out
+
+
 def lde(cols: np.ndarray, log_blowup: int) -> np.ndarray:
     """Matrix::interpolate then Matrix::evaluate on the coset 3*<w_N>."""
     a = np.ascontiguousarray(cols, dtype=np.uint64)

@@ -50,6 +50,8 @@ SIGNATURES = {
     "ss_poly_eval": (c_int, [c_void_p, c_int, c_void_p, c_uint64, c_int, c_int, POINTER(ctypes.c_int32), c_void_p, c_size_t, c_void_p]),
     "ss_ood_eval": (c_int, [c_void_p, c_int, c_void_p, c_uint64, c_int, POINTER(ctypes.c_int32), POINTER(c_uint64), c_size_t, c_void_p, c_uint64, c_uint64, c_void_p]),
     "ss_pow_grind": (c_int, [c_void_p, c_int, POINTER(c_uint8), c_int, POINTER(c_uint64)]),
+    "ss_ntt_shard": (c_int, [c_void_p, c_int, c_void_p, c_uint64, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_uint64, c_void_p]),
+    "ss_shard_dft": (c_int, [c_void_p, c_int, c_void_p, c_uint64, c_void_p, c_uint64, c_uint64, c_int, c_int, c_int, c_uint64, c_void_p]),
     "ss_perm_product": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_uint64, c_uint64, c_void_p, c_void_p, c_void_p, c_uint64, c_void_p]),
     "ss_diluted_aggregate": (c_int, [c_void_p, c_int, c_void_p, c_uint64, c_uint64, c_void_p, c_void_p, c_void_p, c_uint64, c_void_p]),
     "ss_constraint_eval": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_uint64, c_int, c_int, c_int, c_uint64, c_uint64, c_int, c_void_p, c_void_p]),

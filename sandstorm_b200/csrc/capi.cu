@@ -124,6 +124,7 @@ void ss_destroy(ss_ctx *ctx) {
     dev_trim(ctx);
     for (auto &kv : ctx->pool_size) cudaFree(kv.first);       // blocks still held by live trees die with the context
     for (auto &kv : ctx->tables) cudaFree(kv.second);
+    for (auto &kv : ctx->scale_tables) { cudaFree(kv.second.first); cudaFree(kv.second.second); }
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->stage) cudaFreeHost(ctx->stage);
     if (ctx->stage_done) cudaEventDestroy(ctx->stage_done);

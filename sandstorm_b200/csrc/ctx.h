@@ -25,6 +25,8 @@ struct ss_ctx {
     // device blocks released by dev_free, kept for reuse (size -> pointers) and the size of every live block
     std::multimap<size_t, void *> pool_free;
     std::map<void *, size_t> pool_size;
+    // geometric scale tables c * h^k of the sharded transforms, keyed by (log length, c, h) (ntt_host.cu custom_scale)
+    std::map<std::vector<uint32_t>, std::pair<void *, void *>> scale_tables;
     // pinned staging area for small host -> device uploads that must not block the caller (program blobs)
     void *stage = nullptr;
     size_t stage_bytes = 0;

@@ -3,6 +3,7 @@
 #include "ctx.h"
 #include "ntt_fp252.cuh"
 #include <cstdlib>
+#include <cstring>
 
 using namespace ss;
 
@@ -80,7 +81,30 @@ struct NttJob {
     int pre_scale, post_scale; // NttScaleMode
     int scale_variant;
     bool canon_out;
+    const Fp *sc_lo = nullptr, *sc_hi = nullptr;   // explicit two-level scale table (custom_scale) instead of a variant
 };
+
+// lo[i] = c * h^i (i < 4096), hi[i] = h^(4096 i) for an arbitrary geometric scale, cached by value
+// (one device allocation per table pair: .first owns it, .second points into it)
+ss_status custom_scale(ss_ctx *ctx, int log_len, const Fp &c, const Fp &h, const Fp **lo, const Fp **hi) {
+    std::vector<uint32_t> key(17);
+    key[0] = (uint32_t)log_len;
+    for (int i = 0; i < 8; ++i) { key[1 + i] = c.l[i]; key[9 + i] = h.l[i]; }
+    const size_t n = (size_t)1 << log_len, n_lo = n < 4096 ? n : 4096, n_hi = n <= 4096 ? 1 : n / 4096;
+    auto it = ctx->scale_tables.find(key);
+    if (it == ctx->scale_tables.end()) {
+        std::vector<Fp> host(n_lo + n_hi);
+        geometric(host.data(), n_lo, c, h);
+        geometric(host.data() + n_lo, n_hi, fp::one(), fp::pow_u64(h, 4096));
+        void *d = nullptr;
+        SS_CUDA_CHECK(ctx, cudaMalloc(&d, host.size() * sizeof(Fp)));
+        SS_CUDA_CHECK(ctx, cudaMemcpy(d, host.data(), host.size() * sizeof(Fp), cudaMemcpyHostToDevice));
+        it = ctx->scale_tables.emplace(key, std::make_pair(d, static_cast<void *>(nullptr))).first;
+    }
+    *lo = static_cast<const Fp *>(it->second.first);
+    *hi = *lo + n_lo;
+    return SS_OK;
+}
 
 template <bool DIT>
 ss_status launch_pass(ss_ctx *ctx, const NttPass &p, cudaStream_t st) {
@@ -116,7 +140,10 @@ ss_status run_ntt(ss_ctx *ctx, const NttJob &job, cudaStream_t st) {
     if ((rc = cached_table(ctx, {T_LOCAL, 12, inv}, 2048, fill_local, &tw_local))) return rc;
     if ((rc = cached_table(ctx, {T_LO, job.log_n, inv}, n < 4096 ? n : 4096, fill_lo, &tw_lo))) return rc;
     if ((rc = cached_table(ctx, {T_HI, job.log_n, inv}, n <= 4096 ? 1 : n / 4096, fill_hi, &tw_hi))) return rc;
-    if (job.pre_scale != SCALE_NONE || job.post_scale != SCALE_NONE) {
+    if (job.sc_lo) {
+        sc_lo = const_cast<Fp *>(job.sc_lo);
+        sc_hi = const_cast<Fp *>(job.sc_hi);
+    } else if (job.pre_scale != SCALE_NONE || job.post_scale != SCALE_NONE) {
         const bool is_const = job.pre_scale == SCALE_CONST || job.post_scale == SCALE_CONST;
         if ((rc = cached_table(ctx, {T_SCALE_LO, job.log_n, job.scale_variant}, is_const ? 1 : (n < 4096 ? n : 4096), fill_scale_lo, &sc_lo))) return rc;
         if (!is_const)
@@ -176,6 +203,58 @@ ss_status bitrev_permute(ss_ctx *ctx, Fp *cols, uint64_t stride, int n_cols, int
     ctx->launches++;
     SS_CUDA_CHECK(ctx, cudaGetLastError());
     return SS_OK;
+}
+
+// ---- the size-W transform ACROSS ranks of a sharded NTT (W = 2, 4, 8) -------------------------------------------------
+// out[k1][i] = tw(i)^k1 * sum_{j1 < W} in[j1][i] * wW^(j1 k1),   i < count,   tw(i) = base^(tw_offset + i)  (or 1)
+// in / out are W slabs each (base pointer + slab stride).  One thread per i: W loads, a radix-2 network in registers
+// ((W/2) log2 W - trivial multiplications), at most 2 (W - 1) twiddle multiplications, W stores.  HBM-bound:
+// 2 * W * 32 B per thread.
+struct ShardDftArgs {
+    const Fp *in; Fp *out;
+    unsigned long long in_stride, out_stride, count, tw_offset;
+    Fp wpow[4];                     // wW^e, e < W/2 (direction applied)
+    const Fp *tw_lo, *tw_hi;        // base^i (i < 4096), base^(4096 i); nullptr = no twiddle
+};
+
+template <int LOG_W>
+__global__ void __launch_bounds__(256) shard_dft_kernel(const ShardDftArgs A) {
+    constexpr int W = 1 << LOG_W;
+    const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (i >= A.count) return;
+    Fp x[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) x[j] = nttk::ld_stream(A.in + (unsigned long long)j * A.in_stride + i);
+    // DIF network: natural in, bit-reversed out
+#pragma unroll
+    for (int len = W / 2; len >= 1; len >>= 1) {
+#pragma unroll
+        for (int b = 0; b < W; b += 2 * len) {
+#pragma unroll
+            for (int k = 0; k < len; ++k) {
+                const Fp a = x[b + k], c = x[b + k + len];
+                x[b + k] = fp::add(a, c);
+                Fp d = fp::sub(a, c);
+                const int e = k * (W / (2 * len));
+                if (e) d = fp::mul(d, A.wpow[e]);
+                x[b + k + len] = d;
+            }
+        }
+    }
+    Fp t, tk;
+    if (A.tw_lo) { t = nttk::two_level_tw(A.tw_lo, A.tw_hi, A.tw_offset + i); tk = t; }
+#pragma unroll
+    for (int k1 = 0; k1 < W; ++k1) {
+        int pos = 0;                                           // x[brev(k1)] holds output k1
+#pragma unroll
+        for (int bit = 0; bit < LOG_W; ++bit) pos |= ((k1 >> bit) & 1) << (LOG_W - 1 - bit);
+        Fp v = x[pos];
+        if (A.tw_lo && k1 >= 1) {
+            v = fp::mul(v, tk);
+            if (k1 + 1 < W) tk = fp::mul(tk, t);
+        }
+        nttk::st_stream(A.out + (unsigned long long)k1 * A.out_stride + i, fp::canon(v));
+    }
 }
 
 }  // namespace
@@ -264,6 +343,102 @@ ss_status ss_lde(ss_ctx *ctx, ss_field field, const void *d_trace, uint64_t trac
     rc = run_ntt(ctx, fwd, st);
     if (rc) return rc;
     if (out_order == SS_ORDER_BITREV) return bitrev_permute(ctx, fwd.dst, lde_stride, n_cols, log_n + log_blowup, st);
+    return SS_OK;
+}
+
+/* Local part of a transform that is sharded over W ranks (sandstorm_b200/parallel.py): the size-m
+ * transforms between the two all-to-all exchanges, with the geometric scale factors the decomposition needs.
+ *   stages & 1: inverse DIF of size m = 2^log_m, natural -> bit-reversed, output k scaled by c0 * h0^k
+ *               (1/M, the coset shift of this rank's residue class, ... all folded into (c0, h0))
+ *   stages & 2: forward DIT of size m << log_expand from bit-reversed coefficients (zero-padded by interleaving),
+ *               natural output k2 scaled by tw^k2 (the inter-rank twiddle w_M^(j1 k2); NULL = none)
+ * stages = 3 runs both through the context's scratch buffer (the local LDE).  d_dst may equal d_src for stages 1 / 2
+ * without expansion. */
+ss_status ss_ntt_shard(ss_ctx *ctx, ss_field field, const void *d_src, uint64_t src_stride, int n_cols, int log_m, int stages,
+                       int log_expand, const void *h_c0, const void *h_h0, const void *h_tw, void *d_dst, uint64_t dst_stride,
+                       void *stream) {
+    if (!ctx) return SS_ERR_INVALID;
+    if (field != SS_FIELD_FP252) return fail(ctx, SS_ERR_UNSUPPORTED, "ss_ntt_shard: field %d not built", (int)field);
+    if (!d_src || !d_dst || n_cols < 0 || log_m < 0 || log_expand < 0 || log_m + log_expand > 40 || stages < 1 || stages > 3 ||
+        ((stages & 1) && (!h_c0 || !h_h0)) || (!(stages & 2) && log_expand) || src_stride < (1ull << log_m) ||
+        dst_stride < (1ull << (log_m + log_expand)))
+        return fail(ctx, SS_ERR_INVALID, "ss_ntt_shard: bad arguments");
+    if (n_cols == 0) return SS_OK;
+    SS_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = pick_stream(ctx, stream);
+    auto load = [](const void *p) { Fp v; memcpy(v.l, p, 32); return fp::canon(v); };
+    const size_t m = (size_t)1 << log_m;
+    const Fp *coeffs = static_cast<const Fp *>(d_src);
+    uint64_t cstride = src_stride;
+    ss_status rc;
+    if (stages & 1) {
+        NttJob inv{};
+        inv.src = static_cast<const Fp *>(d_src); inv.src_stride = src_stride;
+        if (stages & 2) {
+            void *scratch;
+            if ((rc = scratch_reserve(ctx, (size_t)n_cols * m * sizeof(Fp), &scratch))) return rc;
+            inv.dst = static_cast<Fp *>(scratch); inv.dst_stride = m;
+        } else {
+            inv.dst = static_cast<Fp *>(d_dst); inv.dst_stride = dst_stride;
+        }
+        inv.n_cols = n_cols; inv.log_n = log_m; inv.inverse = true; inv.dit = false;
+        inv.post_scale = SCALE_TABLE_BREV; inv.canon_out = true;
+        if ((rc = custom_scale(ctx, log_m, load(h_c0), load(h_h0), &inv.sc_lo, &inv.sc_hi))) return rc;
+        if (log_m == 0) {
+            // a single element: run_ntt copies; apply the scale c0 through a size-1 "table" is not wired -> handle on the host side
+            return fail(ctx, SS_ERR_UNSUPPORTED, "ss_ntt_shard: log_m must be >= 1");
+        }
+        if ((rc = run_ntt(ctx, inv, st))) return rc;
+        coeffs = inv.dst; cstride = inv.dst_stride;
+    }
+    if (stages & 2) {
+        NttJob fwd{};
+        fwd.dst = static_cast<Fp *>(d_dst); fwd.src = coeffs;
+        fwd.dst_stride = dst_stride; fwd.src_stride = cstride;
+        fwd.n_cols = n_cols; fwd.log_n = log_m + log_expand; fwd.inverse = false; fwd.dit = true;
+        fwd.expand_log = log_expand; fwd.canon_out = true;
+        if (h_tw) {
+            fwd.post_scale = SCALE_TABLE_NAT;
+            if ((rc = custom_scale(ctx, log_m + log_expand, fp::one(), load(h_tw), &fwd.sc_lo, &fwd.sc_hi))) return rc;
+        }
+        if ((rc = run_ntt(ctx, fwd, st))) return rc;
+    }
+    return SS_OK;
+}
+
+/* The size-W transform across the W ranks of a sharded NTT (W = 2^log_w <= 8):
+ *   out[k1 * out_stride + i] = tw(i)^k1 * sum_{j1 < W} in[j1 * in_stride + i] * w_W^(+-j1 k1),    i < count,
+ * with tw(i) = w_M^(+-(tw_offset + i)), M = 2^tw_log_m (tw_log_m < 0: no twiddle); inverse selects the sign of both roots. */
+ss_status ss_shard_dft(ss_ctx *ctx, ss_field field, const void *d_in, uint64_t in_stride, void *d_out, uint64_t out_stride,
+                       uint64_t count, int log_w, int inverse, int tw_log_m, uint64_t tw_offset, void *stream) {
+    if (!ctx) return SS_ERR_INVALID;
+    if (field != SS_FIELD_FP252) return fail(ctx, SS_ERR_UNSUPPORTED, "ss_shard_dft: field %d not built", (int)field);
+    if (!d_in || !d_out || log_w < 1 || log_w > 3 || tw_log_m > 40 || (tw_log_m >= 0 && tw_offset + count > (1ull << tw_log_m)))
+        return fail(ctx, SS_ERR_INVALID, "ss_shard_dft: bad arguments");
+    if (count == 0) return SS_OK;
+    SS_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+    ShardDftArgs A{};
+    A.in = static_cast<const Fp *>(d_in); A.out = static_cast<Fp *>(d_out);
+    A.in_stride = in_stride; A.out_stride = out_stride; A.count = count; A.tw_offset = tw_offset;
+    const Fp w = root_of_unity(log_w, inverse != 0);
+    Fp acc = fp::one();
+    for (int e = 0; e < 4; ++e) { A.wpow[e] = fp::canon(acc); acc = fp::mul(acc, w); }
+    if (tw_log_m >= 0) {
+        Fp *lo, *hi;
+        ss_status rc;
+        const size_t M = (size_t)1 << tw_log_m;
+        const int inv = inverse ? 1 : 0;
+        if ((rc = cached_table(ctx, {T_LO, tw_log_m, inv}, M < 4096 ? M : 4096, fill_lo, &lo))) return rc;
+        if ((rc = cached_table(ctx, {T_HI, tw_log_m, inv}, M <= 4096 ? 1 : M / 4096, fill_hi, &hi))) return rc;
+        A.tw_lo = lo; A.tw_hi = hi;
+    }
+    cudaStream_t st = pick_stream(ctx, stream);
+    const unsigned grid = (unsigned)((count + 255) / 256);
+    if (log_w == 1) shard_dft_kernel<1><<<grid, 256, 0, st>>>(A);
+    else if (log_w == 2) shard_dft_kernel<2><<<grid, 256, 0, st>>>(A);
+    else shard_dft_kernel<3><<<grid, 256, 0, st>>>(A);
+    ctx->launches++;
+    SS_CUDA_CHECK(ctx, cudaGetLastError());
     return SS_OK;
 }
 

@@ -85,7 +85,7 @@ class Matrix:
         n_cols, n = self.num_cols, self.num_rows
         out = torch.empty((n_cols, n << log_blowup, 4), dtype=torch.int64, device=self.data.device)
         coeffs = torch.empty_like(self.data) if keep_coeffs else None
-        c.check(c.lib.ss_lde(c.handle, _lib.FIELD_FP252, ctypes.c_void_p(self.data.data_ptr()), n, n_cols, self.log_rows,
+        c.check(c.lib.ss_lde(c.handle, _lib.FIELD_FP252, ctypes.c_void_p(self.data.data_ptr()), self.col_stride, n_cols, self.log_rows,
                              log_blowup, ctypes.c_void_p(out.data_ptr()), n << log_blowup,
                              ctypes.c_void_p(coeffs.data_ptr()) if keep_coeffs else None, n, out_order, _stream_ptr()))
         lde = Matrix(out, c)

@@ -41,7 +41,7 @@ class MatrixMerkleTree:
                     row_order: int = _lib.ORDER_NATURAL) -> "MatrixMerkleTree":
         c = matrix.ctx
         handle = ctypes.c_void_p()
-        c.check(c.lib.ss_merkle_build(c.handle, kind, n_friendly, ctypes.c_void_p(matrix.data.data_ptr()), matrix.num_rows,
+        c.check(c.lib.ss_merkle_build(c.handle, kind, n_friendly, ctypes.c_void_p(matrix.data.data_ptr()), matrix.col_stride,
                                       matrix.num_cols, matrix.log_rows, row_order, ctypes.byref(handle), _stream_ptr()))
         return cls(handle, matrix, kind, n_friendly, row_order)
 
@@ -87,10 +87,21 @@ class MatrixMerkleTree:
             idx = np.array([int(f"{int(i):0{self.log_rows}b}"[::-1], 2) for i in idx], dtype=np.uint64)
         m = self.matrix
         out = np.zeros((len(idx), m.num_cols, 4), dtype=np.uint64)
-        self.ctx.check(self.ctx.lib.ss_rows_gather(self.ctx.handle, ctypes.c_void_p(m.data.data_ptr()), m.num_rows, m.num_cols,
+        self.ctx.check(self.ctx.lib.ss_rows_gather(self.ctx.handle, ctypes.c_void_p(m.data.data_ptr()), m.col_stride, m.num_cols,
                                                    idx.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), len(idx),
                                                    out.ctypes.data_as(ctypes.c_void_p)))
         return out
 
     def prove_rows(self, indices):
         return {"rows": self.rows(indices), "paths": self.prove(indices)}
+
+    # ---- MerkleTree::verify / MatrixMerkleTree::verify_rows (host side, as in the reference: crypto/src/merkle/mod.rs:125-165, 306-346) ----
+    @staticmethod
+    def verify_rows(kind: int, root: bytes, indices, rows: np.ndarray, paths: np.ndarray, n_friendly: int = NUM_FRIENDLY_COMMITMENT_LAYERS) -> None:
+        """Recomputes the root from the opened rows (uint64[q, n_cols, 4] Montgomery limbs) and their sibling paths
+        (uint8[q, depth, 32], leaf level first, storage form); raises MerkleError on a mismatch."""
+        from .verify import merkle_root_from_opening
+
+        for q, idx in enumerate(indices):
+            if merkle_root_from_opening(kind, int(idx), rows[q], paths[q], n_friendly) != root:
+                raise MerkleError(f"invalid Merkle opening of row {int(idx)}")

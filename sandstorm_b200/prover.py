@@ -133,18 +133,21 @@ class HotPathProver:
         self.timeline: list = []
 
     # ---- what this rank reads of the trace (for callers that stream it from the host) -----------------------------
-    def trace_columns_owned(self) -> list[int]:
-        """trace columns (base then extension) whose LDE this rank computes: it needs them completely."""
-        from .parallel import owned_columns
+    def trace_rows_needed(self) -> list[tuple[int, int]]:
+        """(first row, count) ranges of the trace rows this rank reads of EVERY column: its block-cyclic pieces
+        (parallel.pieces) plus, after each piece, the max_offset rows the out-of-domain dot products reach (wrapping mod n).
+        For callers that stream the trace from host memory (bench.py e2e leg)."""
+        if self.world == 1:
+            return [(0, self.n)]
+        from .parallel import pieces
 
-        nb, ne = self.layout.num_base_columns, self.layout.num_extension_columns
-        return owned_columns(nb, self.rank, self.world) + [nb + j for j in owned_columns(ne, self.rank, self.world)]
-
-    def trace_rows_needed(self) -> tuple[int, int]:
-        """(first row, count) of the trace rows this rank reads of EVERY column (the out-of-domain dot products over its
-        row range reach max_offset rows further; wraps mod n)."""
-        step = self.n // self.world
-        return self.rank * step, min(self.n, step + (self.layout.max_offset if self.world > 1 else 0))
+        out, reach = [], self.layout.max_offset
+        for lo, cnt in pieces(self.log_n, self.rank, self.world):
+            hi = lo + cnt + reach
+            out.append((lo, min(hi, self.n) - lo))
+            if hi > self.n:
+                out.append((0, min(hi - self.n, self.n)))
+        return out
 
     # ---- host-side stand-ins for the public coin -------------------------------------------------------
     def _draw(self) -> int:
@@ -170,9 +173,11 @@ class HotPathProver:
         self._composition_program = self.composition_template().patch(challenges, hints, alpha)
         return self._composition_program
 
-    # ---- commitment helper: whole tree on one GPU, row-range sub-trees + combined root on several ---------
+    # ---- commitment helper: whole tree on one GPU; on several, row-range sub-trees + combined root ----------------------
     def _commit(self, ptr: int, col_stride: int, n_cols: int, log_rows: int):
-        """Returns (root bytes, handle or None).  ptr: device address of column 0, row 0 of the matrix."""
+        """Returns (root bytes, handle).  ptr: device address of column 0, row 0 of the matrix.  With world > 1 this is used
+        for the FRI layers only, whose evaluations every rank holds completely (they are all-gathered), so both the sharded
+        and the small unsharded build read valid rows on every rank."""
         c, opt = self.ctx, self.opt
         world, rank = self.world, self.rank
         shard = world > 1 and log_rows - (world.bit_length() - 1) >= 10
@@ -212,20 +217,17 @@ class HotPathProver:
         and authentication paths (the proof payload) instead of only counting their bytes.
         column_ready(k): optional hook called before trace column k (base then extension; None = all) is first read, so that a
         caller streaming the trace from host memory can order its uploads against the LDE (bench.py e2e leg).
-        With world > 1 (torch.distributed initialised, one process per GPU): LDE and OOD are sharded by column,
-        Merkle hashing / constraint evaluation / DEEP / FRI folds by LDE row range; LDE columns are broadcast
-        from their owners, row-sharded vectors all-gathered, sub-tree roots combined (SURVEY.md §8e plan A)."""
+        With world > 1 the work is row-sharded over the ranks (_prove_sharded)."""
         opt, L = self.opt, self.layout
         assert base.num_cols == L.num_base_columns and base.num_rows == self.n
+        if self.world > 1:
+            return self._prove_sharded(base, ext, hints, column_ready)
         coin = self.coin
-        from .parallel import owned_columns, share_row_ranges
-
         res = HotPathResult()
-        dev, world, rank = self.device, self.world, self.rank
+        dev = self.device
         n, N, b = self.n, self.N, opt.log_blowup
         c = self.ctx = base.ctx
         nb, C = L.num_base_columns, L.num_columns
-        row_lo, row_cnt = rank * (N // world), N // world
         handles = []
         self.mark("start")
         # one matrix for every committed column: trace | composition (ce) | w | u | v  (see __init__)
@@ -234,19 +236,16 @@ class HotPathProver:
         lde = all_lde[:C]
 
         def lde_cols(src: Matrix, first_col: int):
-            for j in owned_columns(src.num_cols, rank, world):
+            for j in range(src.num_cols):
                 if column_ready is not None:
                     column_ready(first_col + j)          # e.g. make the stream wait for the upload of this column
-                c.check(c.lib.ss_lde(c.handle, _lib.FIELD_FP252, ctypes.c_void_p(src.data[j].data_ptr()), n, 1, self.log_n, b,
+                c.check(c.lib.ss_lde(c.handle, _lib.FIELD_FP252, ctypes.c_void_p(src.data[j].data_ptr()), src.col_stride, 1, self.log_n, b,
                                      ctypes.c_void_p(lde[first_col + j].data_ptr()), S, None, n,
                                      _lib.ORDER_NATURAL, None))
 
         # 3-5: base trace
         lde_cols(base, 0)
         self.mark("lde_base")
-        halo = L.max_offset << b                      # forward reach of the constraint taps, in LDE rows
-        share_row_ranges(lde[:nb], world, rank, halo)
-        self.mark("share_base")
         res.roots["base"], h = self._commit(lde.data_ptr(), S, nb, self.log_n + b); handles.append(h)
         self.mark("merkle_base")
         # 6-7: challenges, hints, extension columns
@@ -264,27 +263,17 @@ class HotPathProver:
         # 8: extension trace
         lde_cols(ext, nb)
         self.mark("lde_ext")
-        share_row_ranges(lde[nb:], world, rank, halo)
-        self.mark("share_ext")
         res.roots["ext"], h = self._commit(lde[nb].data_ptr(), S, C - nb, self.log_n + b); handles.append(h)
         self.mark("merkle_ext")
         coin.reseed_with_digest(res.roots["ext"])
-        # 9: constraint evaluation (row range of this rank), boundary denominators from w = 1/(x - 1)
+        # 9: constraint evaluation, boundary denominators from w = 1/(x - 1)
         res.composition_coeffs = [coin.draw()]
         prog = self.composition_program(challenges, res.hints, res.composition_coeffs)
         self.mark("patch")
-        if world == 1:
-            inv_x_minus_c(all_lde[self.w_col], _mont(1), c)
-        else:                                            # only the rows this rank's taps reach
-            lo_w, hi_w = tap_reach(prog.blob, self.log_n + b).get(self.w_col, (0, 0))
-            if hi_w - lo_w >= N // 4:                    # tiny domains: signed offsets are ambiguous, take every row
-                inv_x_minus_c(all_lde[self.w_col], _mont(1), c)
-            else:
-                inv_x_minus_c(all_lde[self.w_col], _mont(1), c, rows=(row_lo + lo_w, min(N, row_cnt + hi_w - lo_w)))
+        inv_x_minus_c(all_lde[self.w_col], _mont(1), c)
         comp_evals = torch.empty((N, 4), dtype=torch.int64, device=dev)
         self.mark("inv_w")
-        evaluate(prog, Matrix(all_lde, c), b, out=comp_evals, rows=(row_lo, row_cnt) if world > 1 else None)
-        self._gather_rows(comp_evals, row_lo, row_cnt)
+        evaluate(prog, Matrix(all_lde, c), b, out=comp_evals)
         self.mark("constraint_eval")
         # 10: composition polynomial -> ce columns (coefficients j, j+ce, ...) -> LDE -> commit
         work = Matrix(comp_evals.view(1, N, 4), c)
@@ -298,40 +287,24 @@ class HotPathProver:
         comp_lde.zero_()
         comp_lde[:, :n] = comp_coeffs
         self.mark("comp_split")
-        if world == 1:
-            Matrix(comp_lde, c).ntt_(coset=True)
-        else:                                            # one composition column per rank, then the row ranges
-            for j in owned_columns(self.ce, rank, world):
-                Matrix(comp_lde[j:j + 1], c).ntt_(coset=True)
-            share_row_ranges(comp_lde, world, rank, 0)
+        Matrix(comp_lde, c).ntt_(coset=True)
         self.mark("ntt_comp_fwd")
         res.roots["composition"], h = self._commit(comp_lde.data_ptr(), S, self.ce, self.log_n + b); handles.append(h)
         self.mark("merkle_comp")
         # 11: out-of-domain evaluations of every tap, straight from the trace (barycentric dot products with one shared
-        #     weight vector, ss_ood_eval).  Each rank sums over its range of trace rows; the partial values add up.
+        #     weight vector, ss_ood_eval)
         coin.reseed_with_digest(res.roots["composition"])
         z = res.ood_point = coin.draw()
         taps = L.taps()
         if column_ready is not None:
             column_ready(None)                           # every trace column is read from here on
-        t_lo, t_cnt = rank * (n // world), n // world
         parts = np.zeros((len(taps), 4), dtype=np.uint64)
         for mat, first, count in ((base, 0, nb), (ext, nb, C - nb)):
             idx = [k for k, (col, _) in enumerate(taps) if first <= col < first + count]
             if idx:
-                parts[idx] = ood_eval(mat, [taps[k][0] - first for k in idx], [taps[k][1] for k in idx], _mont(z),
-                                      rows=(t_lo, t_cnt) if world > 1 else None)
+                parts[idx] = ood_eval(mat, [taps[k][0] - first for k in idx], [taps[k][1] for k in idx], _mont(z))
         to_int = lambda a: [int(r[0]) | int(r[1]) << 64 | int(r[2]) << 128 | int(r[3]) << 192 for r in a]
-        if world > 1:
-            import torch.distributed as dist
-
-            mine = torch.from_numpy(parts.view(np.int64)).to(dev)
-            every = torch.empty((world,) + tuple(mine.shape), dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(every, mine)
-            per_rank = [to_int(a) for a in every.cpu().numpy().view(np.uint64)]
-            ood_m = [sum(vals) % P for vals in zip(*per_rank)]
-        else:
-            ood_m = to_int(parts)
+        ood_m = to_int(parts)
         zc = pow(z, self.ce, P)
         ood_c = poly_eval(Matrix(comp_coeffs, c), list(range(self.ce)), np.stack([_mont(zc)] * self.ce), natural_order=True)
         self.mark("ood")
@@ -342,34 +315,24 @@ class HotPathProver:
         coin.reseed_with_field_elements(res.ood_composition)
         alpha = res.deep_alpha = coin.draw()
         t_terms, c_terms = deep_terms(taps, res.ood_trace, res.ood_composition, self.comp_col, alpha, P)
-        # (the sub-coset evaluation below reads u and v only at rows that are multiples of the blowup)
-        if world == 1:                                   # (launched first: the GPU works while the host compiles)
-            inv_x_minus_c(all_lde[self.u_col], _mont(z), c, log_row_step=b)
-            inv_x_minus_c(all_lde[self.v_col], _mont(zc), c, log_row_step=b)
+        # (the sub-coset evaluation below reads u and v only at rows that are multiples of the blowup; launched first:
+        #  the GPU works while the host compiles)
+        inv_x_minus_c(all_lde[self.u_col], _mont(z), c, log_row_step=b)
+        inv_x_minus_c(all_lde[self.v_col], _mont(zc), c, log_row_step=b)
         deep_prog = compile_program(deep_expr_shifted(t_terms, c_terms, self.u_col, self.v_col, self.g, P), self.log_n, b)
-        if world > 1:
-            reach = tap_reach(deep_prog.blob, self.log_n + b)
-            for col, point in ((self.u_col, z), (self.v_col, zc)):
-                lo_t, hi_t = reach.get(col, (0, 0))
-                first, cnt = (row_lo + lo_t) >> b, min(n, (row_cnt + hi_t - lo_t + (1 << b) - 1) >> b)
-                if hi_t - lo_t >= N // 4:
-                    first, cnt = 0, n
-                inv_x_minus_c(all_lde[col], _mont(point), c, log_row_step=b, rows=(first, cnt))
         del comp_coeffs, comp_evals, work
         # The quotient has degree < n - 1, so its n values on the sub-coset 3<w_n> — the LDE rows that are multiples of
         # the blowup — determine it: evaluate only those (1/blowup of the work), then extend like any other column
         # (coset iNTT of size n, zero padding, coset NTT of size N).  Same polynomial, hence the same N evaluations.
         deep = torch.empty((N, 4), dtype=torch.int64, device=dev)
-        sub_lo, sub_cnt = row_lo >> b, row_cnt >> b
         self.mark("deep_setup")
-        evaluate(deep_prog, Matrix(all_lde, c), b, out=deep[:n], rows=(row_lo, sub_cnt) if world > 1 else None, log_row_step=b)
-        self._gather_rows(deep[:n], sub_lo, sub_cnt)
+        evaluate(deep_prog, Matrix(all_lde, c), b, out=deep[:n], log_row_step=b)
         self.mark("deep")
         Matrix(deep[:n].view(1, n, 4), c).ntt_(inverse=True, coset=True)
         deep[n:].zero_()
         Matrix(deep.view(1, N, 4), c).ntt_(coset=True)
         self.mark("deep_lde")
-        if self_check and world == 1:
+        if self_check:
             # test hook: the extended quotient equals the row-by-row evaluation on the whole LDE coset
             inv_x_minus_c(all_lde[self.u_col], _mont(z), c)
             inv_x_minus_c(all_lde[self.v_col], _mont(zc), c)
@@ -385,11 +348,7 @@ class HotPathProver:
             coin.reseed_with_digest(root)
             fri_alpha = coin.draw()
             res.fri_alphas.append(fri_alpha)
-            shard = world > 1 and rows >= (1 << 16)
-            lo, cnt = (rank * (rows // world), rows // world) if shard else (0, 0)
-            nxt = fri_fold(evals, opt.log_fold, _mont(fri_alpha), _mont(offset), ctx=c, rows=(lo, cnt) if shard else None)
-            if shard:
-                self._gather_rows(nxt, lo, cnt)
+            nxt = fri_fold(evals, opt.log_fold, _mont(fri_alpha), _mont(offset), ctx=c)
             layers.append((handle, evals, log_size))
             evals, log_size, offset = nxt, log_size - opt.log_fold, pow(offset, 1 << opt.log_fold, P)
         res.remainder = evals.cpu().numpy().view(np.uint64)
@@ -400,8 +359,7 @@ class HotPathProver:
         if opt.grinding_factor:
             res.pow_nonce = coin.grind_proof_of_work(opt.grinding_factor, c)
             coin.reseed_with_int(res.pow_nonce)
-        # 15: queries (openings + rows through the ABI) — single-GPU trees only
-        if queries and world == 1:
+        if queries:
             pos = coin.draw_queries(opt.num_queries, N)
             res.query_positions = pos
             idx = np.array(pos, dtype=np.uint64)
@@ -433,6 +391,237 @@ class HotPathProver:
             c.lib.ss_tree_free(handle)
         for h in handles:
             c.lib.ss_tree_free(h)
+        return res
+
+    # ---- the device stages over several GPUs: every transform row-sharded (parallel.ShardedTransforms) ---------------------
+    def _commit_pieces(self, ptr: int, col_stride: int, n_cols: int, my_pieces) -> bytes:
+        """Commitment of a block-cyclic matrix: one sub-tree per owned piece, the W^2 sub-roots all-gathered in row order
+        and combined (ss_merkle_combine); for the Friendly tree the combined levels are Pedersen."""
+        import torch.distributed as dist
+
+        c, opt, W = self.ctx, self.opt, self.world
+        log_w = W.bit_length() - 1
+        friendly = max(0, opt.n_friendly - 2 * log_w) if opt.tree_kind == _lib.TREE_FRIENDLY else 0
+        mine = bytearray()
+        for lo, cnt in my_pieces:
+            handle = ctypes.c_void_p()
+            c.check(c.lib.ss_merkle_build(c.handle, opt.tree_kind, friendly, ctypes.c_void_p(ptr + 32 * lo), col_stride, n_cols,
+                                          cnt.bit_length() - 1, _lib.ORDER_NATURAL, ctypes.byref(handle), None))
+            root = (ctypes.c_uint8 * 32)()
+            c.check(c.lib.ss_merkle_root(c.handle, handle, root))
+            c.lib.ss_tree_free(handle)
+            mine += bytes(root)
+        t = torch.tensor(list(mine), dtype=torch.uint8, device=self.device)
+        every = torch.empty((W, W * 32), dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(every, t)
+        sub = every.view(W, W, 32).permute(1, 0, 2).contiguous().cpu().numpy().tobytes()       # [rank][k1] -> row order [k1][rank]
+        buf = (ctypes.c_uint8 * len(sub)).from_buffer_copy(sub)
+        root = (ctypes.c_uint8 * 32)()
+        c.check(c.lib.ss_merkle_combine(c.handle, opt.tree_kind, buf, 2 * log_w, root))
+        return bytes(root)
+
+    def _gather_pieces(self, vec: torch.Tensor, log_len: int) -> None:
+        """all-gather of a block-cyclic vector, in place: afterwards every rank holds every row."""
+        import torch.distributed as dist
+
+        from .parallel import pieces
+
+        W = self.world
+        ps = pieces(log_len, self.rank, W)
+        s = ps[0][1]
+        mine = torch.cat([vec[lo:lo + cnt] for lo, cnt in ps])                                   # [k1][s]
+        every = torch.empty((W,) + tuple(mine.shape), dtype=vec.dtype, device=vec.device)
+        dist.all_gather_into_tensor(every, mine)
+        vec[:W * W * s].view(W, W, s, *vec.shape[1:]).copy_(every.view(W, W, s, *vec.shape[1:]).permute(1, 0, 2, *range(3, 2 + vec.dim())))
+
+    def _exchange_halo(self, cols: torch.Tensor, log_len: int, halo: int) -> None:
+        """cols: [n_cols, len, 4] block-cyclic.  After the call the `halo` rows that follow each owned piece (wrapping) are
+        valid too: they are the first rows of the next rank's piece, received at their absolute position."""
+        import torch.distributed as dist
+
+        from .parallel import pieces
+
+        if halo == 0:
+            return
+        W, r = self.world, self.rank
+        s = pieces(log_len, r, W)[0][1]
+        if halo > s:                                        # small domains: simply give every rank every row
+            for j in range(cols.shape[0]):
+                self._gather_pieces(cols[j], log_len)
+            return
+        prv, nxt = (r - 1) % W, (r + 1) % W
+        ops, staged = [], []
+        for j in range(cols.shape[0]):
+            for (lo, _), (nlo, _) in zip(pieces(log_len, r, W), pieces(log_len, nxt, W)):
+                ops.append(dist.P2POp(dist.isend, cols[j, lo:lo + halo], prv))
+                ops.append(dist.P2POp(dist.irecv, cols[j, nlo:nlo + halo], nxt))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        del staged
+
+    def _prove_sharded(self, base: Matrix, ext, hints, column_ready) -> HotPathResult:
+        """world > 1 (torch.distributed initialised, one process per GPU).  Every column's transforms are split over the
+        ranks (parallel.ShardedTransforms: two all-to-alls per LDE column, 1/W of the arithmetic per rank whatever the
+        number of columns); each rank ends up with W contiguous row ranges ("pieces") of EVERY column, on which it hashes
+        leaves, evaluates the constraints and the DEEP quotient with no further exchange except a halo of
+        max_offset * blowup rows per piece, the 32-byte sub-roots and the partial out-of-domain sums.  The FRI layers
+        (1/8 of the work of one column and shrinking) run on the all-gathered DEEP evaluations.  Bit-identical to world = 1
+        (tools/check_multi_gpu.py)."""
+        import torch.distributed as dist
+
+        from .parallel import DeviceShardOps, ShardedTransforms, pieces
+
+        opt, L, coin = self.opt, self.layout, self.coin
+        res = HotPathResult()
+        dev, W, rank = self.device, self.world, self.rank
+        n, N, b = self.n, self.N, opt.log_blowup
+        log_n, log_N = self.log_n, self.log_n + b
+        c = self.ctx = base.ctx
+        nb, C = L.num_base_columns, L.num_columns
+        if N // (W * W) < 16 << b:
+            raise ValueError("trace too short to shard over this many GPUs")
+        st = ShardedTransforms(rank, W, DeviceShardOps(c), dev)
+        PN, Pn = pieces(log_N, rank, W), pieces(log_n, rank, W)
+        self.mark("start")
+        S = N + opt.col_pad_rows
+        all_lde = torch.empty((C + self.ce + 3, S, 4), dtype=torch.int64, device=dev)[:, :N]
+        lde = all_lde[:C]
+        halo = L.max_offset << b
+
+        def lde_cols(src: Matrix, first_col: int):
+            for j in range(src.num_cols):
+                if column_ready is not None:
+                    column_ready(first_col + j)
+                st.lde(src.data[j], log_n, b, lde[first_col + j])
+
+        # 3-5: base trace
+        lde_cols(base, 0)
+        self.mark("lde_base")
+        self._exchange_halo(lde[:nb], log_N, halo)
+        self.mark("share_base")
+        res.roots["base"] = self._commit_pieces(lde.data_ptr(), S, nb, PN)
+        self.mark("merkle_base")
+        coin.reseed_with_digest(res.roots["base"])
+        challenges = res.challenges = [coin.draw() for _ in range(L.n_challenges())]
+        if callable(ext):
+            ext = ext(challenges)
+        if hints is None:
+            hints = [coin.draw() for _ in range(L.n_hints())]
+        elif callable(hints):
+            hints = hints(challenges)
+        res.hints = list(hints)
+        self.mark("ext_columns")
+        # 8: extension trace
+        lde_cols(ext, nb)
+        self.mark("lde_ext")
+        self._exchange_halo(lde[nb:], log_N, halo)
+        self.mark("share_ext")
+        res.roots["ext"] = self._commit_pieces(lde[nb].data_ptr(), S, C - nb, PN)
+        self.mark("merkle_ext")
+        coin.reseed_with_digest(res.roots["ext"])
+        # 9: constraint evaluation on the owned pieces
+        res.composition_coeffs = [coin.draw()]
+        prog = self.composition_program(challenges, res.hints, res.composition_coeffs)
+        self.mark("patch")
+        lo_w, hi_w = tap_reach(prog.blob, log_N).get(self.w_col, (0, 0))
+        whole_w = hi_w - lo_w >= N // 4                   # tiny domains: signed offsets are ambiguous, take every row
+        if whole_w:
+            inv_x_minus_c(all_lde[self.w_col], _mont(1), c)
+        comp_evals = torch.empty((N, 4), dtype=torch.int64, device=dev)
+        for lo, cnt in PN:
+            if not whole_w:
+                inv_x_minus_c(all_lde[self.w_col], _mont(1), c, rows=(lo + lo_w, min(N, cnt + hi_w - lo_w)))
+        self.mark("inv_w")
+        for lo, cnt in PN:
+            evaluate(prog, Matrix(all_lde, c), b, out=comp_evals, rows=(lo, cnt))
+        self.mark("constraint_eval")
+        # 10: composition polynomial -> ce interleaved columns -> LDE -> commit (all sharded)
+        assert self.ce == 2
+        comp_lde = all_lde[self.comp_col:self.comp_col + self.ce]
+        shares = st.composition_columns(comp_evals, log_n, b, [comp_lde[0], comp_lde[1]])
+        self.mark("ntt_comp")
+        res.roots["composition"] = self._commit_pieces(comp_lde.data_ptr(), S, self.ce, PN)
+        self.mark("merkle_comp")
+        # 11: out-of-domain values: partial barycentric sums over the owned trace rows, summed over the ranks
+        coin.reseed_with_digest(res.roots["composition"])
+        z = res.ood_point = coin.draw()
+        taps = L.taps()
+        if column_ready is not None:
+            column_ready(None)
+        to_int = lambda a: [int(r[0]) | int(r[1]) << 64 | int(r[2]) << 128 | int(r[3]) << 192 for r in a]
+        rinv = pow(R, -1, P)
+        acc = [0] * len(taps)
+        for mat, first, count in ((base, 0, nb), (ext, nb, C - nb)):
+            idx = [k for k, (col, _) in enumerate(taps) if first <= col < first + count]
+            for lo, cnt in Pn:
+                part = to_int(ood_eval(mat, [taps[k][0] - first for k in idx], [taps[k][1] for k in idx], _mont(z), rows=(lo, cnt)))
+                for k, v in zip(idx, part):
+                    acc[k] = (acc[k] + v) % P
+        # composition columns: each rank evaluates its residue class of the coefficients (coset-scaled, bit-reversed: the
+        # ss_lde coefficient format) at y = z^ce:  sum_j2 x[r + W j2] (y/3)^(r + W j2)
+        zc = pow(z, self.ce, P)
+        y3 = zc * pow(3, -1, P) % P
+        point = 3 * pow(y3, W, P) % P
+        for e in range(self.ce):
+            v = to_int(poly_eval(Matrix(shares[e].view(1, -1, 4), c), [0], np.stack([_mont(point)])))[0]
+            acc.append(v * pow(y3, rank, P) % P)
+        mine = torch.from_numpy(np.array([[(v >> (64 * k)) & 0xFFFFFFFFFFFFFFFF for k in range(4)] for v in acc], dtype=np.uint64).view(np.int64)).to(dev)
+        every = torch.empty((W,) + tuple(mine.shape), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(every, mine)
+        per_rank = [to_int(a) for a in every.cpu().numpy().view(np.uint64)]
+        total = [sum(vals) % P * rinv % P for vals in zip(*per_rank)]
+        res.ood_trace, res.ood_composition = total[:len(taps)], total[len(taps):]
+        self.mark("ood")
+        # 12: DEEP quotient on the owned rows of the sub-coset, then extended like any other column
+        coin.reseed_with_field_elements(res.ood_trace)
+        coin.reseed_with_field_elements(res.ood_composition)
+        alpha = res.deep_alpha = coin.draw()
+        t_terms, c_terms = deep_terms(taps, res.ood_trace, res.ood_composition, self.comp_col, alpha, P)
+        deep_prog = compile_program(deep_expr_shifted(t_terms, c_terms, self.u_col, self.v_col, self.g, P), log_n, b)
+        reach = tap_reach(deep_prog.blob, log_N)
+        for col, point in ((self.u_col, z), (self.v_col, zc)):
+            lo_t, hi_t = reach.get(col, (0, 0))
+            if hi_t - lo_t >= N // 4:
+                inv_x_minus_c(all_lde[col], _mont(point), c, log_row_step=b)
+                continue
+            for lo, cnt in PN:
+                inv_x_minus_c(all_lde[col], _mont(point), c, log_row_step=b, rows=((lo + lo_t) >> b, min(n, (cnt + hi_t - lo_t + (1 << b) - 1) >> b)))
+        deep = torch.empty((N, 4), dtype=torch.int64, device=dev)
+        quotient = torch.empty((n, 4), dtype=torch.int64, device=dev)
+        self.mark("deep_setup")
+        for lo, cnt in PN:
+            evaluate(deep_prog, Matrix(all_lde, c), b, out=quotient, rows=(lo, cnt >> b), log_row_step=b)
+        self.mark("deep")
+        st.lde(quotient, log_n, b, deep, src_on_coset=True)
+        self._gather_pieces(deep, log_N)
+        self.mark("deep_lde")
+        del comp_evals, quotient
+        # 13: FRI layers on the gathered evaluations (row ranges per rank while the layers are large)
+        evals, log_size, offset = deep, log_N, 3
+        layers = []
+        while (1 << log_size) >> b > opt.max_remainder_coeffs and log_size > opt.log_fold:
+            rows = 1 << (log_size - opt.log_fold)
+            root, handle = self._commit(evals.data_ptr(), rows, 1 << opt.log_fold, log_size - opt.log_fold)
+            res.fri_roots.append(root)
+            coin.reseed_with_digest(root)
+            fri_alpha = coin.draw()
+            res.fri_alphas.append(fri_alpha)
+            shard = rows >= (1 << 16)
+            lo, cnt = (rank * (rows // W), rows // W) if shard else (0, 0)
+            nxt = fri_fold(evals, opt.log_fold, _mont(fri_alpha), _mont(offset), ctx=c, rows=(lo, cnt) if shard else None)
+            if shard:
+                self._gather_rows(nxt, lo, cnt)
+            layers.append(handle)
+            evals, log_size, offset = nxt, log_size - opt.log_fold, pow(offset, 1 << opt.log_fold, P)
+        res.remainder = evals.cpu().numpy().view(np.uint64)
+        self.final_domain = (log_size, offset)
+        coin.reseed_with_field_element_vector([v * rinv % P for v in to_int(res.remainder)])
+        self.mark("fri")
+        if opt.grinding_factor:
+            res.pow_nonce = coin.grind_proof_of_work(opt.grinding_factor, c)
+            coin.reseed_with_int(res.pow_nonce)
+        for handle in layers:
+            c.lib.ss_tree_free(handle)
         return res
 
     def stage_ms(self) -> dict:

@@ -215,8 +215,11 @@ def test_specialised_kernels_match_interpreter(ss, oracle, name, log_n):
     cols = torch.from_numpy(oracle.random_felts(rng, C + ce + 3, N).view(np.int64)).cuda()
     m = ss.Matrix(cols)
     c = m.ctx
-    comp = compile_program(L.composition(n, inv_x_minus_one_col=C + ce), log_n, 1, [rnd.randrange(P) for _ in range(L.n_challenges())],
-                           [rnd.randrange(P) for _ in range(L.n_hints())], [rnd.randrange(P)])
+    from sandstorm_b200.air import compile_template
+
+    # the prover's path: challenge-independent template + value patch (hints of a real proof are small: 0, 1, addresses)
+    comp = compile_template(L.composition(n, inv_x_minus_one_col=C + ce), log_n, 1, L.n_challenges(), L.n_hints(), 1).patch(
+        [rnd.randrange(P) for _ in range(L.n_challenges())], [rnd.randrange(3) for _ in range(L.n_hints())], [rnd.randrange(P)])
     g = pow(3, (P - 1) // n, P)
     tt, ct = deep_terms(L.taps(), [rnd.randrange(P) for _ in L.taps()], [rnd.randrange(P) for _ in range(ce)], C, rnd.randrange(P), P)
     deep = compile_program(deep_expr_shifted(tt, ct, C + ce + 1, C + ce + 2, g, P), log_n, 1)

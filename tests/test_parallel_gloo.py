@@ -156,3 +156,141 @@ def test_ownership_helpers():
     assert parallel.row_range(1 << 10, 3, 4) == (768, 1024)
     with pytest.raises(ValueError):
         parallel.row_range(1 << 10, 0, 3)
+
+
+# ---- row-sharded transforms (parallel.ShardedTransforms) with the local kernels replaced by big-int arithmetic -------------
+class BigIntShardOps:
+    """CPU stand-in for parallel.DeviceShardOps with the SAME contract as the C ABI entry points ss_shard_dft /
+    ss_ntt_shard (include/sandstorm_b200.h), on canonical Montgomery tensors [len, 4]."""
+    P = 2**251 + 17 * 2**192 + 1
+    R = 2**256
+
+    def _get(self, t, off, count):
+        a = t.numpy().view(np.uint64)
+        rinv = pow(self.R, -1, self.P)
+        return [(int(a[off + i][0]) | int(a[off + i][1]) << 64 | int(a[off + i][2]) << 128 | int(a[off + i][3]) << 192) * rinv % self.P for i in range(count)]
+
+    def _put(self, t, off, vals):
+        a = t.numpy().view(np.uint64)
+        for i, v in enumerate(vals):
+            m = v % self.P * self.R % self.P
+            a[off + i] = [(m >> (64 * k)) & 0xFFFFFFFFFFFFFFFF for k in range(4)]
+
+    def dft(self, src, src_off, src_stride, dst, dst_off, dst_stride, count, log_w, inverse, tw_log_m, tw_offset):
+        P, W = self.P, 1 << log_w
+        wW = pow(3, (P - 1) >> log_w, P)
+        base = pow(3, (P - 1) >> tw_log_m, P) if tw_log_m >= 0 else 1
+        if inverse:
+            wW, base = pow(wW, -1, P), pow(base, -1, P)
+        x = [self._get(src, src_off + j * src_stride, count) for j in range(W)]
+        for k1 in range(W):
+            out = []
+            for i in range(count):
+                v = sum(x[j][i] * pow(wW, j * k1, P) for j in range(W))
+                out.append(v * pow(base, (tw_offset + i) * k1, P) % P)
+            self._put(dst, dst_off + k1 * dst_stride, out)
+
+    @staticmethod
+    def _brev(v, bits):
+        return int(f"{v:0{bits}b}"[::-1], 2) if bits else 0
+
+    def ntt_shard(self, src, log_m, stages, log_expand, c0, h0, tw, dst):
+        P, m = self.P, 1 << log_m
+        vals = self._get(src, 0, m)
+        if stages & 1:                                   # inverse DIF: natural -> bit-reversed, coefficient k scaled by c0 h0^k
+            wi = pow(3, -((P - 1) >> log_m), P)
+            coef = [sum(vals[j] * pow(wi, j * k, P) for j in range(m)) * c0 * pow(h0, k, P) % P for k in range(m)]
+            vals = [coef[self._brev(p, log_m)] for p in range(m)]
+        if stages & 2:                                   # forward DIT from bit-reversed coefficients, zero-padded
+            mN = m << log_expand
+            w = pow(3, (P - 1) >> (log_m + log_expand), P)
+            coef = [vals[self._brev(k, log_m)] for k in range(m)]
+            out = [sum(coef[j] * pow(w, j * k, P) for j in range(m)) * (pow(tw, k, P) if tw is not None else 1) % P for k in range(mN)]
+            vals = out
+        self._put(dst, 0, vals)
+
+
+def _shard_worker(rank, world, port, trace_np, comp_np, log_n, log_b, q):
+    from sandstorm_b200 import parallel
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        st = parallel.ShardedTransforms(rank, world, BigIntShardOps(), "cpu")
+        n, N = 1 << log_n, 1 << (log_n + log_b)
+        # this rank only sees its pieces of the inputs (everything else is poisoned)
+        def only_mine(full, log_len):
+            t = torch.full_like(torch.from_numpy(full.view(np.int64)), -1)
+            for lo, cnt in parallel.pieces(log_len, rank, world):
+                t[lo:lo + cnt] = torch.from_numpy(full.view(np.int64))[lo:lo + cnt]
+            return t
+        out = {}
+        dst = torch.full((N, 4), -1, dtype=torch.int64)
+        st.lde(only_mine(trace_np, log_n), log_n, log_b, dst)
+        out["lde"] = dst.numpy().view(np.uint64).copy()
+        dst2 = torch.full((N, 4), -1, dtype=torch.int64)
+        st.lde(only_mine(trace_np, log_n), log_n, log_b, dst2, src_on_coset=True)
+        out["lde_coset"] = dst2.numpy().view(np.uint64).copy()
+        cols = [torch.full((N, 4), -1, dtype=torch.int64) for _ in range(2)]
+        shares = st.composition_columns(only_mine(comp_np, log_n + log_b), log_n, log_b, cols)
+        out["comp"] = [c.numpy().view(np.uint64).copy() for c in cols]
+        out["shares"] = [s.numpy().view(np.uint64).copy() for s in shares]
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,log_n,log_b", [(2, 4, 1), (4, 5, 1), (2, 4, 2)])
+def test_row_sharded_transforms_match_the_single_process_definitions(oracle, world, log_n, log_b):
+    """LDE of a trace column, extension of a coset-evaluated column (the DEEP quotient) and the composition-column split,
+    each sharded over `world` gloo ranks with ONE all-to-all per transform side, against the oracle's whole-vector
+    results: every rank must end up with exactly its block-cyclic pieces."""
+    from sandstorm_b200 import parallel
+
+    P = oracle.P
+    n, N = 1 << log_n, 1 << (log_n + log_b)
+    rng = np.random.default_rng(world * 100 + log_n)
+    def coset_interp(evals_mont):                                  # evaluations on 3<w> -> plain coefficients (ints)
+        c = oracle.from_mont(oracle.ntt(evals_mont[None], inverse=True)[0])
+        return [v * pow(3, -k, P) % P for k, v in enumerate(c)]
+
+    def coset_eval(coeffs, size):                                  # plain coefficients -> evaluations on 3<w_size> (Montgomery)
+        a = [c * pow(3, k, P) % P for k, c in enumerate(coeffs)] + [0] * (size - len(coeffs))
+        return oracle.ntt(oracle.to_mont(a)[None])[0]
+
+    trace = oracle.random_felts(rng, 1, n)[0]
+    comp = oracle.random_felts(rng, 1, N)[0]
+    if log_b > 1:                                             # a composition polynomial of degree < 2n, as a valid trace gives
+        comp = coset_eval(coset_interp(comp)[:2 * n], N)
+    want_lde = oracle.lde(trace[None], log_b)[0]
+    want_coset = coset_eval(coset_interp(trace), N)           # a column already on 3<w_n>, extended to 3<w_N>
+    coeffs = coset_interp(comp)
+    want_comp = [coset_eval(coeffs[e:2 * n:2], N) for e in range(2)]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_shard_worker, args=(r, world, port, trace, comp, log_n, log_b, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    poison = np.full(4, 0xFFFFFFFFFFFFFFFF, dtype=np.uint64)
+    for rank, out in results.items():
+        mine = np.zeros(N, dtype=bool)
+        for lo, cnt in parallel.pieces(log_n + log_b, rank, world):
+            mine[lo:lo + cnt] = True
+        for name, want in (("lde", want_lde), ("lde_coset", want_coset)):
+            assert np.array_equal(out[name][mine], want[mine]), (name, rank)
+            assert (out[name][~mine] == poison).all(), f"{name}: rank {rank} wrote rows it does not own"
+        for e in range(2):
+            assert np.array_equal(out["comp"][e][mine], want_comp[e][mine]), ("composition column", e, rank)
+        # the returned coefficient shares: coefficient i = rank + W j2 of column e, scaled by 3^i, at position brev(j2)
+        m = n // world
+        bits = m.bit_length() - 1
+        for e in range(2):
+            got = oracle.from_mont(out["shares"][e])
+            for j2 in range(m):
+                i = rank + world * j2
+                assert got[int(f"{j2:0{bits}b}"[::-1], 2) if bits else 0] == coeffs[2 * i + e] * pow(3, i, P) % P

@@ -69,6 +69,31 @@ def test_hot_path_is_consistent(ss, oracle, layout, log_n, tree):
         assert np.array_equal(res.trace_queries["base"]["rows"][q], lde_base[:, pos])
 
 
+@pytest.mark.parametrize("layout,log_n,tree", [("plain", 7, "keccak_m20"), ("recursive", 12, "friendly"), ("starknet", 16, "keccak_m20")])
+def test_gpu_pipeline_equals_cpu_pipeline(ss, oracle, layout, log_n, tree):
+    """The whole hot path on the GPU against the whole hot path on the CPU (oracle/prover.py: Horner OOD, DEEP quotient on
+    every row from its definition, FRI folds from the definition) with the same coin: every commitment — including the
+    composition root, i.e. constraint evaluation + split — every out-of-domain value, FRI root and the remainder bit for bit."""
+    import torch
+
+    from oracle.prover import CpuHotPath
+    from sandstorm_b200.prover import HotPathProver, ProofOptions, SeededCoin
+
+    gk, ok = (ss.TREE_FRIENDLY, oracle.TREE_FRIENDLY) if tree == "friendly" else (ss.TREE_KECCAK_M20, oracle.TREE_KECCAK_M20)
+    hp = HotPathProver(layout, log_n, ProofOptions(num_queries=8, tree_kind=gk), coin=SeededCoin(77))
+    L = hp.layout
+    rng = np.random.default_rng(1000 + log_n)
+    base = oracle.random_felts(rng, L.num_base_columns, 1 << log_n)
+    ext = oracle.random_felts(rng, L.num_extension_columns, 1 << log_n)
+    got = hp.prove(ss.Matrix.from_numpy(base), ss.Matrix.from_numpy(ext), queries=False)
+    torch.cuda.synchronize()
+    want = CpuHotPath(layout, log_n, tree_kind=ok).prove(base, ext, SeededCoin(77))
+    assert got.roots == want["roots"]
+    assert got.ood_trace == want["ood_trace"] and got.ood_composition == want["ood_composition"]
+    assert got.fri_roots == want["fri_roots"] and len(got.fri_roots) >= 1
+    assert np.array_equal(got.remainder, want["remainder"])
+
+
 def test_ood_values_match_horner(ss, oracle):
     """poly_eval in both coefficient formats against Horner on the oracle's interpolation."""
     from sandstorm_b200.matrix import poly_eval
