@@ -221,6 +221,13 @@ def merkle_build(kind: int, cols: np.ndarray, n_friendly: int = 22, bitrev_rows:
     return nodes, leaves, root.raw
 
 
+def merkle_find_index(hash_kind: int, leaf: bytes, siblings: list, root: bytes) -> int:
+    """index of the opening (leaf, siblings leaf-level-first) under `root`, or -1 (see oracle_merkle_find_index)."""
+    f = lib().oracle_merkle_find_index
+    f.restype = ctypes.c_longlong
+    return int(f(ctypes.c_int(hash_kind), leaf, b"".join(siblings), ctypes.c_int(len(siblings)), root))
+
+
 # ----------------------------------------------------------------- Goldilocks (p = 2^64 - 2^32 + 1), stored words x * 2^64 mod p
 GL_P = 2**64 - 2**32 + 1
 GL_GENERATOR = 7

@@ -170,3 +170,30 @@ void oracle_merkle_root_bytes(int kind, int n_friendly, int n_cols, int log_rows
     fp_from_mont(&c, &m);
     oracle_felt_to_be32(&c, out);
 }
+
+/* Test helper for the reference's proof artefacts (tests/test_reference_proof.py): the leaf index of a Merkle opening is
+ * not part of a serialized proof (the verifier derives it from the public coin); find it by trying both child orders at
+ * every level.  leaf / siblings: 32-byte digests (siblings[0] = sibling leaf, then the path, leaf level first).
+ * Returns the index whose recomputed root equals `root`, or -1. */
+long long oracle_merkle_find_index(int hash_kind, const uint8_t *leaf, const uint8_t *siblings, int depth, const uint8_t *root) {
+    size_t count = 1;
+    uint8_t *cur = (uint8_t *)malloc(32), *nxt;
+    memcpy(cur, leaf, 32);
+    for (int lvl = 0; lvl < depth; ++lvl) {
+        nxt = (uint8_t *)malloc(count * 2 * 32);
+        const uint8_t *s = siblings + 32 * lvl;
+        #pragma omp parallel for schedule(static) if (count >= 1024)
+        for (size_t i = 0; i < count; ++i) {
+            merge_bytes(hash_kind, cur + 32 * i, s, nxt + 32 * i);                    /* index bit lvl = 0: we are the left child */
+            merge_bytes(hash_kind, s, cur + 32 * i, nxt + 32 * (i + count));          /* index bit lvl = 1 */
+        }
+        free(cur);
+        cur = nxt;
+        count *= 2;
+    }
+    long long found = -1;
+    for (size_t i = 0; i < count; ++i)
+        if (!memcmp(cur + 32 * i, root, 32)) { found = (long long)i; break; }
+    free(cur);
+    return found;
+}
