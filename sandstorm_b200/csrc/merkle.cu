@@ -48,14 +48,16 @@ __device__ __forceinline__ void store_digest(uint8_t *dst, const uint32_t (&w)[8
 // Hash of a message made of `n_elems` 32-byte big-endian felts: element e of this message lives at
 // base + e * elem_stride (in Fp units).  Used for rows (elem_stride = column stride) and for the
 // single-column first level (two consecutive leaves).
+// col_bits != 0: message element e is read from column brev_{col_bits}(e) (FRI layer rows, see ss_order).
 template <int BH>
-__device__ __forceinline__ void hash_felts(const Fp *base, unsigned long long elem_stride, int n_elems, uint32_t (&out)[8]) {
+__device__ __forceinline__ void hash_felts(const Fp *base, unsigned long long elem_stride, int n_elems, uint32_t (&out)[8], int col_bits = 0) {
     const uint32_t *w32 = reinterpret_cast<const uint32_t *>(base);
+    auto col = [&](int e) -> unsigned long long { return col_bits ? (unsigned long long)(__brev((unsigned)e) >> (32 - col_bits)) : (unsigned long long)e; };
     if (BH == BH_KECCAK) {
         // message lane g (8 bytes) = big-endian bytes of u64 limb (3 - g%4) of element g/4
         const unsigned long long *w64 = reinterpret_cast<const unsigned long long *>(base);
         auto lane = [&](int g) -> uint64_t {
-            const unsigned long long v = __ldg(w64 + (unsigned long long)(g >> 2) * elem_stride * 4ull + (3 - (g & 3)));
+            const unsigned long long v = __ldg(w64 + col(g >> 2) * elem_stride * 4ull + (3 - (g & 3)));
             return hash::bswap64(v);
         };
         uint64_t d[4];
@@ -65,13 +67,13 @@ __device__ __forceinline__ void hash_felts(const Fp *base, unsigned long long el
     } else if (BH == BH_BLAKE2S) {
         // message word g (LE u32 of 4 message bytes) = bswap32 of u32 limb (7 - g%8) of element g/8
         auto word = [&](int g) -> uint32_t {
-            return hash::bswap32(__ldg(w32 + (unsigned long long)(g >> 3) * elem_stride * 8ull + (7 - (g & 7))));
+            return hash::bswap32(__ldg(w32 + col(g >> 3) * elem_stride * 8ull + (7 - (g & 7))));
         };
         hash::blake2s256_words(word, n_elems * 8, out);
     } else {
         // SHA-256 reads big-endian words: exactly the u32 limb, digest words stored big-endian
         auto word = [&](int g) -> uint32_t {
-            return __ldg(w32 + (unsigned long long)(g >> 3) * elem_stride * 8ull + (7 - (g & 7)));
+            return __ldg(w32 + col(g >> 3) * elem_stride * 8ull + (7 - (g & 7)));
         };
         uint32_t h[8];
         hash::sha256_words(word, n_elems * 8, h);
@@ -80,17 +82,31 @@ __device__ __forceinline__ void hash_felts(const Fp *base, unsigned long long el
     }
 }
 
-// leaf i = H(row src(i)) where src = brev(i) when bitrev.  One thread per row; consecutive threads read
-// consecutive 32-byte elements of each column (coalesced), the row gather across columns is strided.
+// Leaf digests.  Tree leaf p commits matrix row (bitrev ? brev(p) : p).  One thread per ROW in natural order:
+// consecutive threads read consecutive 32-byte elements of each column (coalesced column streams — the 32 * n_cols
+// bytes per row are the kernel's HBM traffic), and the 32-byte digest goes to its leaf slot (a scattered 32-byte
+// sector write when the order is bit-reversed).
 template <int BH>
 __global__ void __launch_bounds__(128) leaf_hash_kernel(const Fp *cols, unsigned long long col_stride, int n_cols,
-                                                          int log_rows, int bitrev, int mask, uint8_t *out) {
+                                                          int log_rows, int bitrev, int col_bits, int mask, uint8_t *out) {
     const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     if (i >> log_rows) return;
-    const unsigned long long src = bitrev ? brev_bits(i, log_rows) : i;
     uint32_t d[8];
-    hash_felts<BH>(cols + src, col_stride, n_cols, d);
-    store_digest(out + 32ull * i, d, mask);
+    hash_felts<BH>(cols + i, col_stride, n_cols, d, col_bits);
+    store_digest(out + 32ull * (bitrev ? brev_bits(i, log_rows) : i), d, mask);
+}
+// The same for a RANGE of tree leaves [leaf_begin, leaf_begin + count), one thread per leaf (ss_hash_rows: the share of
+// one GPU when a commitment is split over several); out[k] = digest of leaf leaf_begin + k.
+template <int BH>
+__global__ void __launch_bounds__(128) leaf_range_hash_kernel(const Fp *cols, unsigned long long col_stride, int n_cols, int log_rows,
+                                                                int bitrev, int col_bits, int mask, unsigned long long leaf_begin,
+                                                                unsigned long long count, uint8_t *out) {
+    const unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const unsigned long long leaf = leaf_begin + k;
+    uint32_t d[8];
+    hash_felts<BH>(cols + (bitrev ? brev_bits(leaf, log_rows) : leaf), col_stride, n_cols, d, col_bits);
+    store_digest(out + 32ull * k, d, mask);
 }
 
 // first level of the single-column variant: node i = H(BE32(leaf 2i) || BE32(leaf 2i+1))
@@ -103,32 +119,77 @@ __global__ void __launch_bounds__(128) leafpair_hash_kernel(const Fp *leaves, un
     store_digest(out + 32ull * i, d, mask);
 }
 
-// node i = H(child 2i || child 2i+1) over raw digest bytes
+// digest of 64 bytes of children held in 16 registers (little-endian u32 words of the 64 bytes)
 template <int BH>
-__global__ void __launch_bounds__(128) node_hash_kernel(const uint8_t *children, unsigned long long count, int mask, uint8_t *out) {
-    const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    uint32_t d[8];
+__device__ __forceinline__ void node_digest(const uint32_t (&c)[16], uint32_t (&d)[8]) {
     if (BH == BH_KECCAK) {
-        const unsigned long long *c = reinterpret_cast<const unsigned long long *>(children + 64ull * i);
-        auto lane = [&](int g) -> uint64_t { return __ldg(c + g); };
+        auto lane = [&](int g) -> uint64_t { return (uint64_t)c[2 * g] | ((uint64_t)c[2 * g + 1] << 32); };
         uint64_t h[4];
         hash::keccak256_lanes(lane, 8, h);
 #pragma unroll
         for (int k = 0; k < 4; ++k) { d[2 * k] = (uint32_t)h[k]; d[2 * k + 1] = (uint32_t)(h[k] >> 32); }
     } else if (BH == BH_BLAKE2S) {
-        const uint32_t *c = reinterpret_cast<const uint32_t *>(children + 64ull * i);
-        auto word = [&](int g) -> uint32_t { return __ldg(c + g); };
+        auto word = [&](int g) -> uint32_t { return c[g]; };
         hash::blake2s256_words(word, 16, d);
     } else {
-        const uint32_t *c = reinterpret_cast<const uint32_t *>(children + 64ull * i);
-        auto word = [&](int g) -> uint32_t { return hash::bswap32(__ldg(c + g)); };
+        auto word = [&](int g) -> uint32_t { return hash::bswap32(c[g]); };
         uint32_t h[8];
         hash::sha256_words(word, 16, h);
 #pragma unroll
         for (int k = 0; k < 8; ++k) d[k] = hash::bswap32(h[k]);
     }
+}
+
+// node i = H(child 2i || child 2i+1) over raw digest bytes
+template <int BH>
+__global__ void __launch_bounds__(128) node_hash_kernel(const uint8_t *children, unsigned long long count, int mask, uint8_t *out) {
+    const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint4 *q = reinterpret_cast<const uint4 *>(children + 64ull * i);
+    uint32_t c[16], d[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const uint4 v = __ldg(q + k); c[4 * k] = v.x; c[4 * k + 1] = v.y; c[4 * k + 2] = v.z; c[4 * k + 3] = v.w; }
+    node_digest<BH>(c, d);
     store_digest(out + 32ull * i, d, mask);
+}
+
+// FUSED_LEVELS tree levels in one launch: a CTA takes 2^FUSED_LEVELS consecutive children (digests at depth dc), keeps the
+// sub-tree above them in shared memory and writes every node it computes to its slot of the node array
+// (node j of depth d lives at nodes[2^d + j]).  One read of the children and one write per node instead of a launch and
+// an HBM round trip per level.
+constexpr int FUSED_LEVELS = 9;
+template <int BH>
+__global__ void __launch_bounds__(256) node_levels_fused_kernel(const uint8_t *children, int dc, int levels, int mask, uint8_t *nodes) {
+    __shared__ uint4 sm[2 << FUSED_LEVELS];                      // 2^levels digests of 32 bytes
+    const unsigned long long per = 1ull << levels;
+    const uint4 *src = reinterpret_cast<const uint4 *>(children) + 2ull * per * blockIdx.x;
+    for (unsigned int k = threadIdx.x; k < 2 * per; k += blockDim.x) sm[k] = __ldg(src + k);
+    __syncthreads();
+    for (int lvl = 1; lvl <= levels; ++lvl) {
+        const unsigned int cnt = 1u << (levels - lvl);           // nodes of this CTA at depth dc - lvl
+        uint32_t d[8];
+        // (reads of level lvl-1 and writes of level lvl both live in sm[0 .. 2 cnt): separate them with barriers)
+        for (unsigned int base = 0; base < cnt; base += blockDim.x) {
+            const unsigned int j = base + threadIdx.x;
+            const bool on = j < cnt;
+            uint32_t c[16];
+            if (on) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { const uint4 v = sm[4 * j + k]; c[4 * k] = v.x; c[4 * k + 1] = v.y; c[4 * k + 2] = v.z; c[4 * k + 3] = v.w; }
+                node_digest<BH>(c, d);
+                if (mask == MASK_KEEP_FIRST20) { d[5] = 0; d[6] = 0; d[7] = 0; }
+                if (mask == MASK_KEEP_LAST20) { d[0] = 0; d[1] = 0; d[2] = 0; }
+            }
+            __syncthreads();                                     // everybody has read its children of this batch
+            if (on) {
+                sm[2 * j] = make_uint4(d[0], d[1], d[2], d[3]);
+                sm[2 * j + 1] = make_uint4(d[4], d[5], d[6], d[7]);
+                uint4 *dst = reinterpret_cast<uint4 *>(nodes + 32ull * ((1ull << (dc - lvl)) + (unsigned long long)cnt * blockIdx.x + j));
+                dst[0] = sm[2 * j]; dst[1] = sm[2 * j + 1];
+            }
+            __syncthreads();
+        }
+    }
 }
 
 __device__ __forceinline__ Fp load_fp(const uint8_t *p) {
@@ -251,6 +312,43 @@ void byte_hash_of(int kind, int &bh, int &mask) {
     }
 }
 
+// node levels above row digests (n_cols >= 2 trees): byte-hash levels FUSED_LEVELS at a time, Pedersen levels one by one
+void build_node_levels(ss_ctx *ctx, ss_tree *t, int bh, int mask, const PedersenTable &tab, cudaStream_t st) {
+    const int height = t->log_rows;
+    const int transition = t->kind == SS_TREE_FRIENDLY ? t->n_friendly : 0;
+    int d = height - 1;                                   // depth of the next level to build
+    while (d >= 0) {
+        const uint8_t *children = (d == height - 1) ? t->d_leaves : t->d_nodes + 64ull * (1ull << d);
+        if (d >= transition) {
+            int levels = d - transition + 1;              // byte-hash levels left
+            if (levels > FUSED_LEVELS) levels = FUSED_LEVELS;
+            if (levels >= 2 && ss::option(ctx, "merkle_fused", 1)) {
+                const unsigned grid = (unsigned)(1ull << (d + 1 - levels));
+                by_byte_hash(bh, [&](auto BH) {
+                    node_levels_fused_kernel<decltype(BH)::value><<<grid, 256, 0, st>>>(children, d + 1, levels, mask, t->d_nodes);
+                    ctx->launches++;
+                    return SS_OK;
+                });
+                d -= levels;
+            } else {
+                const unsigned long long c = 1ull << d;
+                by_byte_hash(bh, [&](auto BH) {
+                    node_hash_kernel<decltype(BH)::value><<<grid_for(c, 128), 128, 0, st>>>(children, c, mask, t->d_nodes + 32ull * c);
+                    ctx->launches++;
+                    return SS_OK;
+                });
+                --d;
+            }
+        } else {
+            const unsigned long long c = 1ull << d;
+            const bool child_high = (d + 1 < transition) && (d != height - 1);
+            pedersen_node_kernel<<<grid_for(c, 128), 128, 0, st>>>(children, c, child_high ? 0 : 1, tab, t->d_nodes + 32ull * c);
+            ctx->launches++;
+            --d;
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -266,7 +364,12 @@ ss_status ss_merkle_build(ss_ctx *ctx, ss_tree_kind kind, int n_friendly, const 
     cudaStream_t st = pick_stream(ctx, stream);
     const unsigned long long n = 1ull << log_rows;
     const Fp *cols = static_cast<const Fp *>(d_cols);
-    const int bitrev = row_order == SS_ORDER_BITREV ? 1 : 0;
+    const int bitrev = ((int)row_order & 1) ? 1 : 0;
+    int col_bits = 0;
+    if ((int)row_order & 2) {                               // SS_ORDER_BITREV_RC: columns in bit-reversed order too
+        while ((1 << col_bits) < n_cols) ++col_bits;
+        if ((1 << col_bits) != n_cols) return fail(ctx, SS_ERR_INVALID, "ss_merkle_build: bit-reversed column order needs a power-of-two column count");
+    }
     int bh, mask;
     byte_hash_of(kind, bh, mask);
     PedersenTable tab{nullptr};
@@ -316,27 +419,11 @@ ss_status ss_merkle_build(ss_ctx *ctx, ss_tree_kind kind, int n_friendly, const 
         }
     } else {
         by_byte_hash(bh, [&](auto BH) {
-            leaf_hash_kernel<decltype(BH)::value><<<grid_for(n, 128), 128, 0, st>>>(cols, col_stride, n_cols, log_rows, bitrev, mask, t->d_leaves);
+            leaf_hash_kernel<decltype(BH)::value><<<grid_for(n, 128), 128, 0, st>>>(cols, col_stride, n_cols, log_rows, bitrev, col_bits, mask, t->d_leaves);
             ctx->launches++;
             return SS_OK;
         });
-        const int transition = kind == SS_TREE_FRIENDLY ? n_friendly : 0;
-        for (int d = height - 1; d >= 0; --d) {
-            const unsigned long long c = 1ull << d;
-            const uint8_t *children = (d == height - 1) ? t->d_leaves : t->d_nodes + 64ull * c;
-            uint8_t *dst = t->d_nodes + 32ull * c;
-            if (d >= transition) {
-                by_byte_hash(bh, [&](auto BH) {
-                    node_hash_kernel<decltype(BH)::value><<<grid_for(c, 128), 128, 0, st>>>(children, c, mask, dst);
-                    ctx->launches++;
-                    return SS_OK;
-                });
-            } else {
-                const bool child_high = (d + 1 < transition) && (d != height - 1);
-                pedersen_node_kernel<<<grid_for(c, 128), 128, 0, st>>>(children, c, child_high ? 0 : 1, tab, dst);
-                ctx->launches++;
-            }
-        }
+        build_node_levels(ctx, t, bh, mask, tab, st);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -345,6 +432,85 @@ ss_status ss_merkle_build(ss_ctx *ctx, ss_tree_kind kind, int n_friendly, const 
     }
     (void)rc;
     *out = t;
+    return SS_OK;
+}
+
+ss_status ss_hash_rows(ss_ctx *ctx, ss_tree_kind kind, const void *d_cols, uint64_t col_stride, int n_cols, int log_rows,
+                       ss_order order, uint64_t leaf_begin, uint64_t leaf_count, void *d_out, void *stream) {
+    if (!ctx) return SS_ERR_INVALID;
+    if (!d_cols || !d_out || n_cols < 2 || log_rows < 0 || log_rows > 40 || col_stride < (1ull << log_rows) || (int)kind < 0 ||
+        (int)kind > SS_TREE_SHA256 || leaf_begin + leaf_count > (1ull << log_rows))
+        return fail(ctx, SS_ERR_INVALID, "ss_hash_rows: bad arguments");
+    if (leaf_count == 0) return SS_OK;
+    int col_bits = 0;
+    if ((int)order & 2) {
+        while ((1 << col_bits) < n_cols) ++col_bits;
+        if ((1 << col_bits) != n_cols) return fail(ctx, SS_ERR_INVALID, "ss_hash_rows: bit-reversed column order needs a power-of-two column count");
+    }
+    SS_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+    int bh, mask;
+    byte_hash_of(kind, bh, mask);
+    by_byte_hash(bh, [&](auto BH) {
+        leaf_range_hash_kernel<decltype(BH)::value><<<grid_for(leaf_count, 128), 128, 0, pick_stream(ctx, stream)>>>(
+            static_cast<const Fp *>(d_cols), col_stride, n_cols, log_rows, (int)order & 1, col_bits, mask, leaf_begin, leaf_count, static_cast<uint8_t *>(d_out));
+        ctx->launches++;
+        return SS_OK;
+    });
+    SS_CUDA_CHECK(ctx, cudaGetLastError());
+    return SS_OK;
+}
+
+ss_status ss_merkle_build_from_leaves(ss_ctx *ctx, ss_tree_kind kind, int n_friendly, const void *d_leaf_digests, int log_rows,
+                                      ss_tree **out, void *stream) {
+    if (!ctx) return SS_ERR_INVALID;
+    if (!out || !d_leaf_digests || log_rows < 1 || log_rows > 40 || (int)kind < 0 || (int)kind > SS_TREE_SHA256 || n_friendly < 0)
+        return fail(ctx, SS_ERR_INVALID, "ss_merkle_build_from_leaves: bad arguments");
+    *out = nullptr;
+    SS_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = pick_stream(ctx, stream);
+    const unsigned long long n = 1ull << log_rows;
+    int bh, mask;
+    byte_hash_of(kind, bh, mask);
+    PedersenTable tab{nullptr};
+    if (kind == SS_TREE_FRIENDLY && n_friendly > 0) {
+        ss_status rc = pedersen_table(ctx, &tab);
+        if (rc) return rc;
+    }
+    ss_tree *t = new ss_tree{ctx, (int)kind, n_friendly, log_rows, 2, nullptr, nullptr};
+    cudaError_t e1 = dev_alloc(ctx, reinterpret_cast<void **>(&t->d_leaves), n * 32), e2 = dev_alloc(ctx, reinterpret_cast<void **>(&t->d_nodes), n * 32);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+        dev_free(ctx, t->d_leaves); dev_free(ctx, t->d_nodes); delete t;
+        cudaGetLastError();
+        return fail(ctx, SS_ERR_OOM, "ss_merkle_build_from_leaves: cannot allocate %llu bytes for the tree", n * 64ull);
+    }
+    cudaMemsetAsync(t->d_nodes, 0, 32, st);
+    cudaMemcpyAsync(t->d_leaves, d_leaf_digests, n * 32, cudaMemcpyDeviceToDevice, st);
+    build_node_levels(ctx, t, bh, mask, tab, st);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        dev_free(ctx, t->d_leaves); dev_free(ctx, t->d_nodes); delete t;
+        return fail(ctx, SS_ERR_CUDA, "ss_merkle_build_from_leaves: launch failed: %s", cudaGetErrorString(e));
+    }
+    *out = t;
+    return SS_OK;
+}
+
+// In-place bit-reversal permutation of 2^log_n 32-byte items (leaf digests moving between row order and tree order)
+__global__ void bitrev32_kernel(uint4 *items, int log_n) {
+    const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (i >> log_n) return;
+    const unsigned long long j = log_n ? (__brevll(i) >> (64 - log_n)) : 0ull;
+    if (i < j) {
+        const uint4 a0 = items[2 * i], a1 = items[2 * i + 1], b0 = items[2 * j], b1 = items[2 * j + 1];
+        items[2 * i] = b0; items[2 * i + 1] = b1; items[2 * j] = a0; items[2 * j + 1] = a1;
+    }
+}
+ss_status ss_bitrev_permute32(ss_ctx *ctx, void *d_items, int log_n, void *stream) {
+    if (!ctx || !d_items || log_n < 0 || log_n > 40) return SS_ERR_INVALID;
+    SS_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+    bitrev32_kernel<<<grid_for(1ull << log_n, 256), 256, 0, pick_stream(ctx, stream)>>>(static_cast<uint4 *>(d_items), log_n);
+    ctx->launches++;
+    SS_CUDA_CHECK(ctx, cudaGetLastError());
     return SS_OK;
 }
 

@@ -47,6 +47,10 @@ from .matrix import Matrix, fri_fold, inv_x_minus_c, ood_eval, poly_eval
 R = 2**256
 
 
+def _brev(v: int, bits: int) -> int:
+    return int(f"{v:0{bits}b}"[::-1], 2) if bits else 0
+
+
 def _mont(v: int) -> np.ndarray:
     m = v % P * R % P
     return np.array([(m >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
@@ -174,7 +178,7 @@ class HotPathProver:
         return self._composition_program
 
     # ---- commitment helper: whole tree on one GPU; on several, row-range sub-trees + combined root ----------------------
-    def _commit(self, ptr: int, col_stride: int, n_cols: int, log_rows: int):
+    def _commit(self, ptr: int, col_stride: int, n_cols: int, log_rows: int, order: int = _lib.ORDER_BITREV):
         """Returns (root bytes, handle).  ptr: device address of column 0, row 0 of the matrix.  With world > 1 this is used
         for the FRI layers only, whose evaluations every rank holds completely (they are all-gathered), so both the sharded
         and the small unsharded build read valid rows on every rank."""
@@ -188,8 +192,16 @@ class HotPathProver:
         friendly = 0
         if opt.tree_kind == _lib.TREE_FRIENDLY:
             friendly = max(0, opt.n_friendly - (world.bit_length() - 1)) if shard else opt.n_friendly
-        c.check(c.lib.ss_merkle_build(c.handle, opt.tree_kind, friendly, ctypes.c_void_p(ptr + 32 * lo), col_stride, n_cols,
-                                      cnt.bit_length() - 1, _lib.ORDER_NATURAL, ctypes.byref(handle), None))
+        if shard:
+            # this rank's range of TREE leaves (leaf p = row brev(p)): digests, then the sub-tree over them
+            leaves = torch.empty((cnt, 4), dtype=torch.int64, device=self.device)
+            c.check(c.lib.ss_hash_rows(c.handle, opt.tree_kind, ctypes.c_void_p(ptr), col_stride, n_cols, log_rows, order, lo, cnt,
+                                       ctypes.c_void_p(leaves.data_ptr()), None))
+            c.check(c.lib.ss_merkle_build_from_leaves(c.handle, opt.tree_kind, friendly, ctypes.c_void_p(leaves.data_ptr()), cnt.bit_length() - 1,
+                                                      ctypes.byref(handle), None))
+        else:
+            c.check(c.lib.ss_merkle_build(c.handle, opt.tree_kind, friendly, ctypes.c_void_p(ptr), col_stride, n_cols, log_rows, order,
+                                          ctypes.byref(handle), None))
         root = (ctypes.c_uint8 * 32)()
         c.check(c.lib.ss_merkle_root(c.handle, handle, root))
         if shard:
@@ -199,6 +211,14 @@ class HotPathProver:
             buf = (ctypes.c_uint8 * (32 * world)).from_buffer_copy(b"".join(subs))
             c.check(c.lib.ss_merkle_combine(c.handle, opt.tree_kind, buf, world.bit_length() - 1, root))
         return bytes(root), handle
+
+    def _remainder(self, evals: torch.Tensor, log_blowup: int) -> np.ndarray:
+        """last FRI layer (natural order on offset<w_m>) -> the coefficients of f(offset * X), degree < m / blowup."""
+        m = evals.shape[0]
+        coeffs = Matrix(evals.clone().view(1, m, 4), self.ctx).ntt_(inverse=True).data[0]
+        keep = max(1, m >> log_blowup)
+        self.remainder_high_zero = not bool(coeffs[keep:].any().item())       # a low-degree codeword: the dropped half vanishes
+        return coeffs[:keep].cpu().numpy().view(np.uint64)
 
     def _gather_rows(self, full: torch.Tensor, lo: int, cnt: int):
         """all-gather of a row-sharded vector: every rank contributes full[lo:lo+cnt]."""
@@ -337,22 +357,24 @@ class HotPathProver:
             inv_x_minus_c(all_lde[self.u_col], _mont(z), c)
             inv_x_minus_c(all_lde[self.v_col], _mont(zc), c)
             res.deep_matches_full_evaluation = bool(torch.equal(deep, evaluate(deep_prog, Matrix(all_lde, c), b)))
-        # 13: FRI layers
+        # 13: FRI layers.  Conventions pinned by the reference's proof artefacts (sandstorm_b200/verify.py): a layer commits, in
+        #     bit-reversed row order, rows of the `fold` evaluations that fold together (ORDER_BITREV_RC on the evaluation
+        #     buffer viewed with col_stride = rows: no data movement); the fold has no 1/fold factor; the remainder is sent as
+        #     the coefficients of f(offset * X).
         evals, log_size, offset = deep, self.log_n + b, 3
         layers = []
         while (1 << log_size) >> b > opt.max_remainder_coeffs and log_size > opt.log_fold:
             rows = 1 << (log_size - opt.log_fold)
-            # the layer matrix (rows x fold) is the evaluation buffer viewed with col_stride = rows
-            root, handle = self._commit(evals.data_ptr(), rows, 1 << opt.log_fold, log_size - opt.log_fold)
+            root, handle = self._commit(evals.data_ptr(), rows, 1 << opt.log_fold, log_size - opt.log_fold, _lib.ORDER_BITREV_RC)
             res.fri_roots.append(root)
             coin.reseed_with_digest(root)
             fri_alpha = coin.draw()
             res.fri_alphas.append(fri_alpha)
-            nxt = fri_fold(evals, opt.log_fold, _mont(fri_alpha), _mont(offset), ctx=c)
+            nxt = fri_fold(evals, opt.log_fold, _mont(fri_alpha), _mont(offset), starkware_scale=True, ctx=c)
             layers.append((handle, evals, log_size))
             evals, log_size, offset = nxt, log_size - opt.log_fold, pow(offset, 1 << opt.log_fold, P)
-        res.remainder = evals.cpu().numpy().view(np.uint64)
         self.final_domain = (log_size, offset)
+        res.remainder = self._remainder(evals, b)
         coin.reseed_with_field_element_vector([v * rinv % P for v in to_int(res.remainder)])
         self.mark("fri")
         # 14: proof of work (GPU search for the smallest nonce), 15: query positions
@@ -360,32 +382,39 @@ class HotPathProver:
             res.pow_nonce = coin.grind_proof_of_work(opt.grinding_factor, c)
             coin.reseed_with_int(res.pow_nonce)
         if queries:
+            # a position is a LEAF index: leaf p of every trace tree commits the LDE row brev(p) (bit-reversed commitment)
             pos = coin.draw_queries(opt.num_queries, N)
             res.query_positions = pos
+            log_N = self.log_n + b
             idx = np.array(pos, dtype=np.uint64)
+            nat = np.array([_brev(p, log_N) for p in pos], dtype=np.uint64)
             for name, h, (first, ncols) in zip(("base", "ext", "composition"), handles, ((0, nb), (nb, C - nb), (self.comp_col, self.ce))):
-                paths = np.zeros((len(idx), self.log_n + b, 32), dtype=np.uint8)
+                paths = np.zeros((len(idx), log_N, 32), dtype=np.uint8)
                 c.check(c.lib.ss_merkle_open(c.handle, h, idx.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), len(idx),
                                              paths.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))))
                 rows_out = np.zeros((len(idx), ncols, 4), dtype=np.uint64)
                 c.check(c.lib.ss_rows_gather(c.handle, ctypes.c_void_p(all_lde[first].data_ptr()), S, ncols,
-                                             idx.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), len(idx), rows_out.ctypes.data_as(ctypes.c_void_p)))
+                                             nat.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), len(nat), rows_out.ctypes.data_as(ctypes.c_void_p)))
                 res.opened_bytes += paths.nbytes + rows_out.nbytes
                 if keep_openings:
                     res.trace_queries[name] = {"rows": rows_out, "paths": paths}
+            F = 1 << opt.log_fold
+            col_perm = [_brev(j, opt.log_fold) for j in range(F)]
             for handle, layer_evals, ls in layers:
-                rows = 1 << (ls - opt.log_fold)
-                idx = np.array(sorted({p % rows for p in pos}), dtype=np.uint64)
-                paths = np.zeros((len(idx), ls - opt.log_fold, 32), dtype=np.uint8)
+                log_rows = ls - opt.log_fold
+                rows = 1 << log_rows
+                pos = sorted({p >> opt.log_fold for p in pos})               # leaf indices of this layer
+                idx = np.array(pos, dtype=np.uint64)
+                nat = np.array([_brev(r, log_rows) for r in pos], dtype=np.uint64)
+                paths = np.zeros((len(idx), log_rows, 32), dtype=np.uint8)
                 c.check(c.lib.ss_merkle_open(c.handle, handle, idx.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), len(idx),
                                              paths.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))))
                 res.opened_bytes += paths.nbytes
                 if keep_openings:
-                    rows_out = np.zeros((len(idx), 1 << opt.log_fold, 4), dtype=np.uint64)
-                    c.check(c.lib.ss_rows_gather(c.handle, ctypes.c_void_p(layer_evals.data_ptr()), rows, 1 << opt.log_fold,
-                                                 idx.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), len(idx), rows_out.ctypes.data_as(ctypes.c_void_p)))
-                    res.fri_layers.append({"positions": [int(p) for p in idx], "rows": rows_out, "paths": paths})
-                pos = [int(p) for p in idx]
+                    rows_out = np.zeros((len(idx), F, 4), dtype=np.uint64)
+                    c.check(c.lib.ss_rows_gather(c.handle, ctypes.c_void_p(layer_evals.data_ptr()), rows, F,
+                                                 nat.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), len(nat), rows_out.ctypes.data_as(ctypes.c_void_p)))
+                    res.fri_layers.append({"positions": pos, "rows": np.ascontiguousarray(rows_out[:, col_perm]), "paths": paths})
             self.mark("queries")
         for handle, _, _ in layers:
             c.lib.ss_tree_free(handle)
@@ -394,30 +423,53 @@ class HotPathProver:
         return res
 
     # ---- the device stages over several GPUs: every transform row-sharded (parallel.ShardedTransforms) ---------------------
-    def _commit_pieces(self, ptr: int, col_stride: int, n_cols: int, my_pieces) -> bytes:
-        """Commitment of a block-cyclic matrix: one sub-tree per owned piece, the W^2 sub-roots all-gathered in row order
-        and combined (ss_merkle_combine); for the Friendly tree the combined levels are Pedersen."""
+    def _commit_pieces(self, cols: torch.Tensor, col_stride: int, log_rows: int) -> bytes:
+        """Commitment of a block-cyclic matrix in the reference's (bit-reversed) leaf order.  A rank owns contiguous row
+        ranges, but tree leaf p commits row brev(p), so a rank's rows are spread over the whole tree: every rank hashes the
+        rows it owns, the 32-byte leaf digests are redistributed with one all-to-all (row i goes to the rank that owns leaf
+        brev(i), i.e. brev_W(i mod W): 1/n_cols of the matrix traffic), each rank builds the sub-tree over its contiguous
+        range of N / W leaves, and the W sub-roots are all-gathered and combined (ss_merkle_combine; Pedersen levels for
+        the Friendly tree).  A single-column matrix is committed with raw leaves (the elements themselves travel)."""
         import torch.distributed as dist
 
-        c, opt, W = self.ctx, self.opt, self.world
+        from .parallel import _all_to_all, pieces
+
+        c, opt, W, r = self.ctx, self.opt, self.world, self.rank
         log_w = W.bit_length() - 1
-        friendly = max(0, opt.n_friendly - 2 * log_w) if opt.tree_kind == _lib.TREE_FRIENDLY else 0
-        mine = bytearray()
-        for lo, cnt in my_pieces:
-            handle = ctypes.c_void_p()
-            c.check(c.lib.ss_merkle_build(c.handle, opt.tree_kind, friendly, ctypes.c_void_p(ptr + 32 * lo), col_stride, n_cols,
-                                          cnt.bit_length() - 1, _lib.ORDER_NATURAL, ctypes.byref(handle), None))
-            root = (ctypes.c_uint8 * 32)()
-            c.check(c.lib.ss_merkle_root(c.handle, handle, root))
-            c.lib.ss_tree_free(handle)
-            mine += bytes(root)
-        t = torch.tensor(list(mine), dtype=torch.uint8, device=self.device)
-        every = torch.empty((W, W * 32), dtype=torch.uint8, device=self.device)
-        dist.all_gather_into_tensor(every, t)
-        sub = every.view(W, W, 32).permute(1, 0, 2).contiguous().cpu().numpy().tobytes()       # [rank][k1] -> row order [k1][rank]
-        buf = (ctypes.c_uint8 * len(sub)).from_buffer_copy(sub)
+        N = 1 << log_rows
+        s = N // (W * W)
+        n_cols, ptr = cols.shape[0], cols.data_ptr()             # cols: [n_cols, N, 4] view of the working matrix
+        D = torch.empty((W, s, 4), dtype=torch.int64, device=self.device)             # my rows' leaves, natural order
+        for k1, (lo, cnt) in enumerate(pieces(log_rows, r, W)):
+            if n_cols == 1:
+                D[k1].copy_(cols[0, lo:lo + cnt])
+            else:
+                c.check(c.lib.ss_hash_rows(c.handle, opt.tree_kind, ctypes.c_void_p(ptr), col_stride, n_cols, log_rows, _lib.ORDER_NATURAL, lo, cnt,
+                                           ctypes.c_void_p(D[k1].data_ptr()), None))
+        # row i = k1 m + r s + u W + c  ->  rank brev_W(c); as [k1][u][c] the c axis selects the destination
+        by_c = D.view(W, s // W, W, 4)
+        send = torch.stack([by_c[:, :, _brev(q, log_w)] for q in range(W)])              # [dest][k1][u]
+        recv = torch.empty_like(send)                                                    # [src][k1][u]
+        _all_to_all(recv.view(W, -1, 4), send.view(W, -1, 4), W)
+        # j = i >> log W = k1 (m / W) + src (s / W) + u in natural order, then to tree order: local leaf = brev(j)
+        leaves = recv.permute(1, 0, 2, 3).contiguous().view(N // W, 4)
+        c.check(c.lib.ss_bitrev_permute32(c.handle, ctypes.c_void_p(leaves.data_ptr()), log_rows - log_w, None))
+        friendly = max(0, opt.n_friendly - log_w) if opt.tree_kind == _lib.TREE_FRIENDLY else 0
+        handle = ctypes.c_void_p()
+        if n_cols == 1:
+            c.check(c.lib.ss_merkle_build(c.handle, opt.tree_kind, friendly, ctypes.c_void_p(leaves.data_ptr()), N // W, 1, log_rows - log_w,
+                                          _lib.ORDER_NATURAL, ctypes.byref(handle), None))
+        else:
+            c.check(c.lib.ss_merkle_build_from_leaves(c.handle, opt.tree_kind, friendly, ctypes.c_void_p(leaves.data_ptr()), log_rows - log_w,
+                                                      ctypes.byref(handle), None))
         root = (ctypes.c_uint8 * 32)()
-        c.check(c.lib.ss_merkle_combine(c.handle, opt.tree_kind, buf, 2 * log_w, root))
+        c.check(c.lib.ss_merkle_root(c.handle, handle, root))
+        c.lib.ss_tree_free(handle)
+        from .parallel import gather_subroots
+
+        subs = gather_subroots(bytes(root), W, self.device)
+        buf = (ctypes.c_uint8 * (32 * W)).from_buffer_copy(b"".join(subs))
+        c.check(c.lib.ss_merkle_combine(c.handle, opt.tree_kind, buf, log_w, root))
         return bytes(root)
 
     def _gather_pieces(self, vec: torch.Tensor, log_len: int) -> None:
@@ -499,7 +551,7 @@ class HotPathProver:
         self.mark("lde_base")
         self._exchange_halo(lde[:nb], log_N, halo)
         self.mark("share_base")
-        res.roots["base"] = self._commit_pieces(lde.data_ptr(), S, nb, PN)
+        res.roots["base"] = self._commit_pieces(lde[:nb], S, log_N)
         self.mark("merkle_base")
         coin.reseed_with_digest(res.roots["base"])
         challenges = res.challenges = [coin.draw() for _ in range(L.n_challenges())]
@@ -516,7 +568,7 @@ class HotPathProver:
         self.mark("lde_ext")
         self._exchange_halo(lde[nb:], log_N, halo)
         self.mark("share_ext")
-        res.roots["ext"] = self._commit_pieces(lde[nb].data_ptr(), S, C - nb, PN)
+        res.roots["ext"] = self._commit_pieces(lde[nb:C], S, log_N)
         self.mark("merkle_ext")
         coin.reseed_with_digest(res.roots["ext"])
         # 9: constraint evaluation on the owned pieces
@@ -540,7 +592,7 @@ class HotPathProver:
         comp_lde = all_lde[self.comp_col:self.comp_col + self.ce]
         shares = st.composition_columns(comp_evals, log_n, b, [comp_lde[0], comp_lde[1]])
         self.mark("ntt_comp")
-        res.roots["composition"] = self._commit_pieces(comp_lde.data_ptr(), S, self.ce, PN)
+        res.roots["composition"] = self._commit_pieces(comp_lde, S, log_N)
         self.mark("merkle_comp")
         # 11: out-of-domain values: partial barycentric sums over the owned trace rows, summed over the ranks
         coin.reseed_with_digest(res.roots["composition"])
@@ -596,25 +648,25 @@ class HotPathProver:
         self._gather_pieces(deep, log_N)
         self.mark("deep_lde")
         del comp_evals, quotient
-        # 13: FRI layers on the gathered evaluations (row ranges per rank while the layers are large)
+        # 13: FRI layers on the gathered evaluations (tree-leaf / row ranges per rank while the layers are large)
         evals, log_size, offset = deep, log_N, 3
         layers = []
         while (1 << log_size) >> b > opt.max_remainder_coeffs and log_size > opt.log_fold:
             rows = 1 << (log_size - opt.log_fold)
-            root, handle = self._commit(evals.data_ptr(), rows, 1 << opt.log_fold, log_size - opt.log_fold)
+            root, handle = self._commit(evals.data_ptr(), rows, 1 << opt.log_fold, log_size - opt.log_fold, _lib.ORDER_BITREV_RC)
             res.fri_roots.append(root)
             coin.reseed_with_digest(root)
             fri_alpha = coin.draw()
             res.fri_alphas.append(fri_alpha)
             shard = rows >= (1 << 16)
             lo, cnt = (rank * (rows // W), rows // W) if shard else (0, 0)
-            nxt = fri_fold(evals, opt.log_fold, _mont(fri_alpha), _mont(offset), ctx=c, rows=(lo, cnt) if shard else None)
+            nxt = fri_fold(evals, opt.log_fold, _mont(fri_alpha), _mont(offset), starkware_scale=True, ctx=c, rows=(lo, cnt) if shard else None)
             if shard:
                 self._gather_rows(nxt, lo, cnt)
             layers.append(handle)
             evals, log_size, offset = nxt, log_size - opt.log_fold, pow(offset, 1 << opt.log_fold, P)
-        res.remainder = evals.cpu().numpy().view(np.uint64)
         self.final_domain = (log_size, offset)
+        res.remainder = self._remainder(evals, b)
         coin.reseed_with_field_element_vector([v * rinv % P for v in to_int(res.remainder)])
         self.mark("fri")
         if opt.grinding_factor:

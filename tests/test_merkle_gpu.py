@@ -157,3 +157,52 @@ def test_sharded_commit_combines_to_the_whole_tree(ss, oracle, name, n_friendly,
     buf = (ctypes.c_uint8 * 128).from_buffer_copy(subs)
     c.check(c.lib.ss_merkle_combine(c.handle, gk, buf, 2, root))
     assert bytes(root) == want
+
+
+@pytest.mark.parametrize("name,n_friendly", [("keccak_m20", 0), ("friendly", 3), ("friendly", 22)])
+def test_leaf_ranges_trees_from_leaves_and_fri_row_order(ss, oracle, name, n_friendly):
+    """The pieces a multi-GPU commitment is made of: digests of ranges of tree leaves (ss_hash_rows) in the three orders,
+    a tree over digests computed elsewhere (ss_merkle_build_from_leaves), the 32-byte bit-reversal permutation, and the FRI
+    layer order (rows and columns bit-reversed) — against the oracle's tree of the explicitly reordered matrix."""
+    import ctypes
+
+    import torch
+
+    from sandstorm_b200 import _lib
+
+    gk, ok = kind_ids(ss, oracle, name)
+    rng = np.random.default_rng(77)
+    log_rows, n_cols = 11, 8
+    n = 1 << log_rows
+    cols = oracle.random_felts(rng, n_cols, n)
+    m = ss.Matrix.from_numpy(cols)
+    c = m.ctx
+    perm = [int(f"{j:03b}"[::-1], 2) for j in range(n_cols)]
+    for order, ref_cols, ref_bitrev in ((_lib.ORDER_NATURAL, cols, False), (_lib.ORDER_BITREV, cols, True), (_lib.ORDER_BITREV_RC, cols[perm], True)):
+        nodes, leaves, root = oracle.merkle_build(ok, np.ascontiguousarray(ref_cols), n_friendly=n_friendly, bitrev_rows=ref_bitrev)
+        got = torch.zeros((n, 4), dtype=torch.int64, device="cuda")
+        for lo, cnt in ((0, 5), (5, 1019), (1024, 1024)):
+            c.check(c.lib.ss_hash_rows(c.handle, gk, ctypes.c_void_p(m.data.data_ptr()), m.col_stride, n_cols, log_rows, order, lo, cnt,
+                                       ctypes.c_void_p(got[lo].data_ptr()), None))
+        torch.cuda.synchronize()
+        assert np.array_equal(got.cpu().numpy().view(np.uint8).reshape(n, 32), leaves)
+        handle = ctypes.c_void_p()
+        c.check(c.lib.ss_merkle_build_from_leaves(c.handle, gk, n_friendly, ctypes.c_void_p(got.data_ptr()), log_rows, ctypes.byref(handle), None))
+        out = (ctypes.c_uint8 * 32)()
+        c.check(c.lib.ss_merkle_root(c.handle, handle, out))
+        c.lib.ss_tree_free(handle)
+        assert bytes(out) == root
+        # the whole-matrix entry point in the same order
+        from sandstorm_b200.merkle import MatrixMerkleTree
+
+        assert MatrixMerkleTree.from_matrix(m, gk, n_friendly=n_friendly, row_order=order).root() == root
+    # natural-order digests -> tree order by the in-place permutation
+    nat = torch.zeros((n, 4), dtype=torch.int64, device="cuda")
+    c.check(c.lib.ss_hash_rows(c.handle, gk, ctypes.c_void_p(m.data.data_ptr()), m.col_stride, n_cols, log_rows, _lib.ORDER_NATURAL, 0, n,
+                               ctypes.c_void_p(nat.data_ptr()), None))
+    c.check(c.lib.ss_bitrev_permute32(c.handle, ctypes.c_void_p(nat.data_ptr()), log_rows, None))
+    want = torch.zeros((n, 4), dtype=torch.int64, device="cuda")
+    c.check(c.lib.ss_hash_rows(c.handle, gk, ctypes.c_void_p(m.data.data_ptr()), m.col_stride, n_cols, log_rows, _lib.ORDER_BITREV, 0, n,
+                               ctypes.c_void_p(want.data_ptr()), None))
+    torch.cuda.synchronize()
+    assert torch.equal(nat, want)

@@ -38,8 +38,9 @@ def test_hot_path_is_consistent(ss, oracle, layout, log_n, tree):
     # the DEEP quotient, evaluated on the sub-coset 3<w_n> and extended, equals its evaluation on every LDE row
     assert res.deep_matches_full_evaluation is True
     # commitments
-    assert res.roots["base"] == oracle.merkle_build(ok, oracle.lde(base, 1))[2]
-    assert res.roots["ext"] == oracle.merkle_build(ok, oracle.lde(ext, 1))[2]
+    # (rows are committed in bit-reversed order of the LDE domain: the reference's convention, tests/test_reference_proof.py)
+    assert res.roots["base"] == oracle.merkle_build(ok, oracle.lde(base, 1), bitrev_rows=True)[2]
+    assert res.roots["ext"] == oracle.merkle_build(ok, oracle.lde(ext, 1), bitrev_rows=True)[2]
     # out-of-domain values: every tap of the mask against Horner evaluation of the oracle's interpolation at z * g^offset
     coeffs = [oracle.from_mont(c) for c in oracle.ntt(np.concatenate([base, ext]), inverse=True)]
     taps = L.taps()
@@ -54,19 +55,22 @@ def test_hot_path_is_consistent(ss, oracle, layout, log_n, tree):
     # the composition columns: commitment of their LDE, and the opened rows at the query positions are rows of that LDE
     comp_rows = res.trace_queries["composition"]["rows"]
     assert comp_rows.shape == (len(res.query_positions), 2, 4)
-    # FRI remainder: evaluations on offset * <w_m> of a polynomial of degree < m / blowup
+    # FRI remainder: the coefficients of f(offset * X) for the last layer's codeword, whose upper half vanished
     log_m, offset = hp.final_domain
-    m = 1 << log_m
     rem = oracle.from_mont(res.remainder)
-    assert len(rem) == m
-    cfs = oracle.from_mont(oracle.ntt(oracle.to_mont(rem)[None], inverse=True)[0])      # coefficients of f(offset * x)
-    assert all(v == 0 for v in cfs[m // 2:]), "FRI remainder is not low-degree"
-    assert any(v != 0 for v in cfs[: m // 2])
+    assert len(rem) == (1 << log_m) >> 1 and any(rem) and hp.remainder_high_zero is True
     assert len(res.fri_roots) >= 1 and res.opened_bytes > 0
-    # opened base rows are the LDE rows at the query positions
+    # opened base rows: leaf p commits the LDE row brev(p)
     lde_base = oracle.lde(base, 1)
+    bits = log_n + 1
     for q, pos in enumerate(res.query_positions[:4]):
-        assert np.array_equal(res.trace_queries["base"]["rows"][q], lde_base[:, pos])
+        assert np.array_equal(res.trace_queries["base"]["rows"][q], lde_base[:, int(f"{pos:0{bits}b}"[::-1], 2)])
+    # every opening verifies on the host against the committed root (MatrixMerkleTree::verify_rows)
+    from sandstorm_b200.merkle import MatrixMerkleTree
+
+    for name in ("base", "ext", "composition"):
+        tq = res.trace_queries[name]
+        MatrixMerkleTree.verify_rows(gk, res.roots[name], res.query_positions[:3], tq["rows"][:3], tq["paths"][:3])
 
 
 @pytest.mark.parametrize("layout,log_n,tree", [("plain", 7, "keccak_m20"), ("recursive", 12, "friendly"), ("starknet", 16, "keccak_m20")])
@@ -91,7 +95,7 @@ def test_gpu_pipeline_equals_cpu_pipeline(ss, oracle, layout, log_n, tree):
     assert got.roots == want["roots"]
     assert got.ood_trace == want["ood_trace"] and got.ood_composition == want["ood_composition"]
     assert got.fri_roots == want["fri_roots"] and len(got.fri_roots) >= 1
-    assert np.array_equal(got.remainder, want["remainder"])
+    assert np.array_equal(got.remainder, want["remainder"]) and want["remainder_high_zero"] and hp.remainder_high_zero
 
 
 def test_ood_values_match_horner(ss, oracle):
