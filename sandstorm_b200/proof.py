@@ -208,3 +208,67 @@ class Proof:
         if o != len(data):
             raise ValueError(f"{len(data) - o} trailing bytes")
         return cls(*opts, trace_len, base_root, ext_root, comp_root, layers, remainder, nonce, bv, ev, cv, bp, ep, cp, ood_t, ood_c, friendly)
+
+
+# ---- assembling a Proof from the prover's result (sandstorm_b200/prover.py HotPathResult with keep_openings=True) ---------------
+_R = 2**256
+_RINV = pow(_R, -1, P)
+
+
+def _felts(arr) -> list:
+    """uint64[..., 4] Montgomery limbs -> canonical ints (flattened, row-major)."""
+    a = arr.reshape(-1, 4)
+    return [(int(r[0]) | int(r[1]) << 64 | int(r[2]) << 128 | int(r[3]) << 192) * _RINV % P for r in a]
+
+
+def _wire_digest(raw: bytes, algebraic: bool):
+    """storage form (csrc/merkle.cu: byte digest, or Montgomery limbs of a Pedersen felt) -> wire form (bytes / canonical int)"""
+    return int.from_bytes(raw, "little") * _RINV % P if algebraic else bytes(raw)
+
+
+def _merkle_proofs(kind, n_friendly, rows, paths, row_digest) -> list:
+    """rows: uint64[q, n_cols, 4]; paths: uint8[q, depth, 32] as ss_merkle_open returns them (sibling leaf, then sibling nodes)."""
+    from . import _lib
+
+    friendly = kind == _lib.TREE_FRIENDLY
+    q, n_cols = rows.shape[0], rows.shape[1]
+    height = paths.shape[1]
+    out = []
+    for k in range(q):
+        if n_cols == 1:
+            leaf, sibling = _felts(rows[k])[0], int.from_bytes(bytes(paths[k, 0]), "little") * _RINV % P
+            path = [_wire_digest(bytes(paths[k, j]), friendly) for j in range(1, height)]
+            out.append(MerkleProof(UNHASHED, path, sibling, leaf))
+        else:
+            path = [_wire_digest(bytes(paths[k, j]), friendly and height - j < n_friendly) for j in range(1, height)]
+            out.append(MerkleProof(HASHED, path, bytes(paths[k, 0]), row_digest(kind, _felts(rows[k]))))
+    return out
+
+
+def assemble_proof(res, options, trace_len: int) -> Proof:
+    """options: prover.ProofOptions; res: HotPathResult of prove(..., keep_openings=True).  Roots of Friendly trees travel as
+    MixedMerkleDigest::HighLevel felts (their `as_bytes` is the big-endian canonical integer ss_merkle_root returns)."""
+    from . import _lib
+    from .verify import row_digest
+
+    kind, nf = options.tree_kind, options.n_friendly
+    friendly = kind == _lib.TREE_FRIENDLY
+
+    def root(b: bytes, log_rows: int, n_cols: int):
+        return int.from_bytes(b, "big") if friendly and (n_cols == 1 or nf > 0) else b
+
+    log_N = (trace_len << options.log_blowup).bit_length() - 1
+    tq = res.trace_queries
+    layers = []
+    for k, lay in enumerate(res.fri_layers):
+        layers.append(FriLayerProof(_felts(lay["rows"]), _merkle_proofs(kind, nf, lay["rows"], lay["paths"], row_digest),
+                                    root(res.fri_roots[k], 0, 1 << options.log_fold)))
+    return Proof(options.num_queries, 1 << options.log_blowup, options.grinding_factor, 1 << options.log_fold, options.max_remainder_coeffs, trace_len,
+                 root(res.roots["base"], log_N, tq["base"]["rows"].shape[1]),
+                 root(res.roots["ext"], log_N, tq["ext"]["rows"].shape[1]) if "ext" in res.roots else None,
+                 root(res.roots["composition"], log_N, 2), layers, _felts(res.remainder), res.pow_nonce,
+                 _felts(tq["base"]["rows"]), _felts(tq["ext"]["rows"]), _felts(tq["composition"]["rows"]),
+                 _merkle_proofs(kind, nf, tq["base"]["rows"], tq["base"]["paths"], row_digest),
+                 _merkle_proofs(kind, nf, tq["ext"]["rows"], tq["ext"]["paths"], row_digest),
+                 _merkle_proofs(kind, nf, tq["composition"]["rows"], tq["composition"]["paths"], row_digest),
+                 list(res.ood_trace), list(res.ood_composition), friendly)

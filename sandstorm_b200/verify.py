@@ -147,3 +147,154 @@ def remainder_at(coeffs, y: int, offset: int) -> int:
     for c in reversed(coeffs):
         acc = (acc * t + c) % P
     return acc
+
+
+# ---- the verifier: `Stark::verify` (ministark, not vendored) restated on the conventions above -----------------------------
+class VerificationError(Exception):
+    pass
+
+
+def _as_bytes(d) -> bytes:
+    """Digest::as_bytes: byte digests verbatim, a Pedersen felt as its big-endian canonical integer."""
+    return d.to_bytes(32, "big") if isinstance(d, int) else bytes(d)
+
+
+def _evaluate_at(e, z, tap_values, log_n, challenges, hints, coeffs):
+    """the composition constraint at an out-of-domain point, Trace(col, off) := the claimed T_col(z g^off)."""
+    import sys
+
+    n = 1 << log_n
+    memo = {}
+
+    def go(e):
+        if e in memo:
+            return memo[e]
+        op = e.op
+        if op == "x": v = z
+        elif op == "const": v = e.args[0]
+        elif op == "trace": v = tap_values[(e.args[0], e.args[1])]
+        elif op == "challenge": v = challenges[e.args[0]]
+        elif op == "hint": v = hints[e.args[0]]
+        elif op == "composition_coeff": v = coeffs[e.args[0]]
+        elif op == "periodic":
+            cs, interval = e.args
+            y, v = pow(z, n // interval, P), 0
+            for c in reversed(cs):
+                v = (v * y + c) % P
+        elif op == "pow": v = pow(go(e.args[0]), e.args[1], P)
+        elif op == "neg": v = -go(e.args[0]) % P
+        else:
+            a, b = go(e.args[0]), go(e.args[1])
+            v = (a + b if op == "add" else a - b if op == "sub" else a * b if op == "mul" else a * pow(b, -1, P)) % P
+        memo[e] = v
+        return v
+
+    sys.setrecursionlimit(max(sys.getrecursionlimit(), 100000))
+    return go(e)
+
+
+def verify_proof(proof, layout, coin, gen_hints, tree_kind: int, n_friendly: int = 22, ce: int = 2) -> None:
+    """Checks a Proof (sandstorm_b200/proof.py) of `layout` against a freshly seeded public coin: transcript, out-of-domain
+    consistency of the composition polynomial, every Merkle opening, the DEEP quotient at every query and the FRI folds down
+    to the remainder.  gen_hints: callable(challenges) -> hints (AirConfig::gen_hints over the public input).
+    Raises VerificationError."""
+    def need(cond, msg):
+        if not cond:
+            raise VerificationError(msg)
+
+    n, b = proof.trace_len, proof.lde_blowup_factor
+    log_n, log_b = n.bit_length() - 1, b.bit_length() - 1
+    N, log_N = n * b, log_n + log_b
+    F = proof.fri_folding_factor
+    log_f = F.bit_length() - 1
+    nb, ne = layout.num_base_columns, layout.num_extension_columns
+    # transcript
+    coin.reseed_with_digest(_as_bytes(proof.base_root))
+    challenges = [coin.draw() for _ in range(layout.n_challenges())]
+    hints = list(gen_hints(challenges))
+    if proof.ext_root is not None:
+        coin.reseed_with_digest(_as_bytes(proof.ext_root))
+    comp_coeffs = [coin.draw()]
+    coin.reseed_with_digest(_as_bytes(proof.comp_root))
+    z = coin.draw()
+    taps = layout.taps()
+    need(len(proof.ood_trace) == len(taps) and len(proof.ood_comp) == ce, "wrong number of out-of-domain values")
+    # out-of-domain consistency: C(z) = sum_j z^j comp_j(z^ce)
+    lhs = _evaluate_at(layout.composition(n), z, dict(zip(taps, proof.ood_trace)), log_n, challenges, hints, comp_coeffs)
+    need(lhs == sum(pow(z, j, P) * v for j, v in enumerate(proof.ood_comp)) % P, "out-of-domain evaluations are inconsistent with the AIR")
+    coin.reseed_with_field_elements(proof.ood_trace)
+    coin.reseed_with_field_elements(proof.ood_comp)
+    deep_alpha = coin.draw()
+    alphas = []
+    for layer in proof.fri_layers:
+        coin.reseed_with_digest(_as_bytes(layer.commitment))
+        alphas.append(coin.draw())
+    coin.reseed_with_field_element_vector(proof.remainder_coeffs)
+    if proof.grinding_factor:
+        need(coin.verify_proof_of_work(proof.grinding_factor, proof.pow_nonce), "proof of work")
+        coin.reseed_with_int(proof.pow_nonce)
+    positions = coin.draw_queries(proof.num_queries, N)
+    q = len(positions)
+    need(len(proof.base_proofs) == q and len(proof.comp_proofs) == q and len(proof.base_values) == q * nb
+         and len(proof.ext_values) == q * ne and len(proof.comp_values) == q * ce, "wrong number of query openings")
+    # trace openings
+    def check_tree(root, proofs, values, width, what):
+        for k, p in enumerate(positions):
+            mp, row = proofs[k], values[width * k:width * (k + 1)]
+            if width == 1:
+                need(mp.variant == 1 and mp.leaf == row[0], f"{what}: opened value differs from the proof's leaf")
+                got = root_from_leaf(tree_kind, p, mp.leaf, mp.sibling, mp.path, n_friendly, unhashed=True)
+            else:
+                need(mp.variant == 0 and mp.leaf == row_digest(tree_kind, row), f"{what}: row hash differs from the proof's leaf")
+                got = root_from_leaf(tree_kind, p, mp.leaf, mp.sibling, mp.path, n_friendly)
+            need(got == _as_bytes(root), f"{what}: Merkle opening of position {p} does not match the commitment")
+
+    check_tree(proof.base_root, proof.base_proofs, proof.base_values, nb, "base trace")
+    if ne:
+        check_tree(proof.ext_root, proof.ext_proofs, proof.ext_values, ne, "extension trace")
+    check_tree(proof.comp_root, proof.comp_proofs, proof.comp_values, ce, "composition trace")
+    # DEEP quotient at the query points (src/lib.rs:102-116: powers of one alpha over the trace arguments, then the composition columns)
+    g, w = pow(3, (P - 1) >> log_n, P), pow(3, (P - 1) >> log_N, P)
+    zc = pow(z, ce, P)
+    deep_at = {}
+    for k, p in enumerate(positions):
+        x = 3 * pow(w, brev(p, log_N), P) % P
+        row = proof.base_values[nb * k:nb * (k + 1)] + proof.ext_values[ne * k:ne * (k + 1)]
+        acc, a = 0, 1
+        inv = {}
+        for (col, off), y in zip(taps, proof.ood_trace):
+            if off not in inv:
+                inv[off] = pow((x - z * pow(g, off, P)) % P, -1, P)
+            acc = (acc + a * (row[col] - y) % P * inv[off]) % P
+            a = a * deep_alpha % P
+        vinv = pow((x - zc) % P, -1, P)
+        for j, y in enumerate(proof.ood_comp):
+            acc = (acc + a * (proof.comp_values[ce * k + j] - y) % P * vinv) % P
+            a = a * deep_alpha % P
+        deep_at[p] = acc
+    # FRI
+    n_layers = len(proof.fri_layers)
+    expect_layers, size = 0, N
+    while size // b > proof.fri_max_remainder_coeffs and size > F:
+        expect_layers, size = expect_layers + 1, size // F
+    need(n_layers == expect_layers and len(proof.remainder_coeffs) == max(1, size // b), "wrong number of FRI layers / remainder coefficients")
+    values = dict(deep_at)                                  # entry index -> value, for the current layer
+    cur_pos, log_dom, offset = positions, log_N, 3
+    for l, layer in enumerate(proof.fri_layers):
+        rows = sorted({p >> log_f for p in cur_pos})
+        need(len(layer.proofs) == len(rows) and len(layer.flattened_rows) == F * len(rows), f"FRI layer {l}: wrong number of openings")
+        nxt = {}
+        for k, r in enumerate(rows):
+            vals, mp = layer.flattened_rows[F * k:F * (k + 1)], layer.proofs[k]
+            need(mp.leaf == row_digest(tree_kind, vals), f"FRI layer {l}: row hash differs from the proof's leaf")
+            need(root_from_leaf(tree_kind, r, mp.leaf, mp.sibling, mp.path, n_friendly) == _as_bytes(layer.commitment),
+                 f"FRI layer {l}: Merkle opening of row {r} does not match the commitment")
+            for j in range(F):
+                if F * r + j in values:
+                    need(values[F * r + j] == vals[j], f"FRI layer {l}: entry {F * r + j} is not the value folded from the layer above")
+            nxt[r] = fri_fold_row(vals, r, log_dom, offset, alphas[l], log_f)
+        values, cur_pos, log_dom, offset = nxt, rows, log_dom - log_f, pow(offset, F, P)
+    wl = pow(3, (P - 1) >> log_dom, P)
+    for r, v in values.items():
+        y = offset * pow(wl, brev(r, log_dom), P) % P
+        need(remainder_at(proof.remainder_coeffs, y, offset) == v, f"FRI remainder does not match the last fold at entry {r}")

@@ -92,3 +92,41 @@ def test_example_trace_through_the_hot_path(example, oracle, log_blowup):
     hp2 = HotPathProver("recursive", log_n, ProofOptions(num_queries=16, log_blowup=log_blowup, tree_kind=ss.TREE_FRIENDLY, grinding_factor=8), coin=coin2)
     res2 = hp2.prove(base, lambda ch: build_extension_columns("recursive", base, ch), hints=tr.gen_hints, queries=False)
     assert res2.roots == res.roots and res2.fri_roots == res.fri_roots and res2.pow_nonce == res.pow_nonce
+
+
+@pytest.mark.parametrize("claim", ["cairo_verifier", "eth_verifier"])
+def test_proof_of_the_example_verifies(example, oracle, claim):
+    """prove -> assemble the `Proof` -> wire format round trip -> verify with a freshly seeded coin (the restated
+    `Stark::verify`: transcript, OOD consistency with the AIR, every opening, DEEP at every query, FRI down to the remainder);
+    a flipped opened value, OOD value or FRI entry must be rejected.  Claims as in src/claims.rs:24-32 (recursive layout)."""
+    import torch
+
+    import sandstorm_b200 as ss
+    from sandstorm_b200.ext_columns import build_extension_columns
+    from sandstorm_b200.proof import Proof, assemble_proof
+    from sandstorm_b200.prover import HotPathProver, ProofOptions
+    from sandstorm_b200.public_coin import CairoVerifierPublicCoin, SolidityVerifierPublicCoin
+    from sandstorm_b200.verify import VerificationError, verify_proof
+
+    tr, log_n = example, 18
+    Coin, kind = (CairoVerifierPublicCoin, ss.TREE_FRIENDLY) if claim == "cairo_verifier" else (SolidityVerifierPublicCoin, ss.TREE_KECCAK)
+    opt = ProofOptions(num_queries=12, log_blowup=1, tree_kind=kind, grinding_factor=10, max_remainder_coeffs=16)
+    hp = HotPathProver("recursive", log_n, opt, coin=Coin.from_public_input(tr.public_input))
+    base = ss.Matrix.from_numpy(to_mont_cols(tr.base_columns))
+    res = hp.prove(base, lambda ch: build_extension_columns("recursive", base, ch), hints=tr.gen_hints, keep_openings=True)
+    torch.cuda.synchronize()
+    proof = assemble_proof(res, opt, tr.trace_len)
+    wire = proof.serialize()
+    again = Proof.deserialize(wire, friendly=proof.friendly)
+    assert again.serialize() == wire and len(wire) < 400_000
+    verify_proof(again, hp.layout, Coin.from_public_input(tr.public_input), tr.gen_hints, kind)
+    # tampering
+    for field, idx in (("base_values", 3), ("ood_trace", 7), ("remainder_coeffs", 0)):
+        bad = Proof.deserialize(wire, friendly=proof.friendly)
+        getattr(bad, field)[idx] = (getattr(bad, field)[idx] + 1) % P
+        with pytest.raises(VerificationError):
+            verify_proof(bad, hp.layout, Coin.from_public_input(tr.public_input), tr.gen_hints, kind)
+    bad = Proof.deserialize(wire, friendly=proof.friendly)
+    bad.fri_layers[1].flattened_rows[2] = (bad.fri_layers[1].flattened_rows[2] + 1) % P
+    with pytest.raises(VerificationError):
+        verify_proof(bad, hp.layout, Coin.from_public_input(tr.public_input), tr.gen_hints, kind)

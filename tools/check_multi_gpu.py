@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Multi-GPU parity check (run under torchrun, one process per GPU): the sharded hot path (world > 1) must produce
 the same commitments, out-of-domain values, FRI roots and remainder as the single-GPU path on the same seeded trace.
-    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/check_multi_gpu.py [layout] [log_n]"""
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/check_multi_gpu.py [layout] [log_n] [keccak_m20|friendly]"""
 import os
 import sys
 
@@ -11,12 +11,14 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import sandstorm_b200 as ss  # noqa: E402
-from sandstorm_b200.prover import HotPathProver  # noqa: E402
+from sandstorm_b200.prover import HotPathProver, ProofOptions  # noqa: E402
 
 
 def main():
     layout = sys.argv[1] if len(sys.argv) > 1 else "starknet"
     log_n = int(sys.argv[2]) if len(sys.argv) > 2 else 18
+    tree = sys.argv[3] if len(sys.argv) > 3 else "keccak_m20"
+    kind = ss.TREE_FRIENDLY if tree == "friendly" else ss.TREE_KECCAK_M20
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -28,14 +30,14 @@ def main():
         t[:, :, 3] &= (1 << 58) - 1
         return t
 
-    sharded = HotPathProver(layout, log_n, rank=rank, world=world)
+    sharded = HotPathProver(layout, log_n, ProofOptions(tree_kind=kind), rank=rank, world=world)
     L = sharded.layout
     base, ext = rand_cols(L.num_base_columns, 1 << log_n), rand_cols(L.num_extension_columns, 1 << log_n)
     got = sharded.prove(ss.Matrix(base), ss.Matrix(ext), queries=False)
     torch.cuda.synchronize()
     ok = True
     if rank == 0:
-        single = HotPathProver(layout, log_n, rank=0, world=1)
+        single = HotPathProver(layout, log_n, ProofOptions(tree_kind=kind), rank=0, world=1)
         want = single.prove(ss.Matrix(base), ss.Matrix(ext), queries=False)
         torch.cuda.synchronize()
         checks = {"roots": got.roots == want.roots, "fri_roots": got.fri_roots == want.fri_roots, "ood_trace": got.ood_trace == want.ood_trace,
