@@ -212,7 +212,7 @@ class FullHotPath:
         self.ctx = ss.default_context()
         t0 = time.perf_counter()
         # challenge-independent structure pass (per layout and trace length); the per-proof value patch runs INSIDE the step
-        self.prover.composition_template()
+        self.prover.prepare()
         self.compile_s = time.perf_counter() - t0
         self.events = self.prover.timeline
         self.last = None

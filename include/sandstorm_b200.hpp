@@ -161,7 +161,8 @@ class MatrixMerkleTree {
     // MerkleTree::prove(indices): sibling paths, leaf level first
     std::vector<Digest> prove(const std::vector<uint64_t> &indices) const {
         std::vector<Digest> out(indices.size() * matrix_.log_rows());
-        matrix_.context().check(ss_merkle_open(matrix_.context().get(), tree_.get(), indices.data(), indices.size(), out[0].data()));
+        if (out.empty()) return out;                      // nothing to open (and out.data() may be null)
+        matrix_.context().check(ss_merkle_open(matrix_.context().get(), tree_.get(), indices.data(), indices.size(), out.data()->data()));
         return out;
     }
     // MatrixMerkleTree::prove_rows(indices): (rows, paths)

@@ -81,3 +81,43 @@ def deep_terms(taps, ood_trace, ood_composition, first_comp_col: int, alpha: int
         c_terms.append((first_comp_col + j, y, pow(alpha, k, p)))
         k += 1
     return t_terms, c_terms
+
+
+def deep_expr_symbolic(taps, n_comp: int, first_comp_col: int, u_col: int, v_col: int, g: int, p: int) -> Expr:
+    """deep_expr_shifted with the per-proof values left open, for `compile_template`: Challenge(0) = the DEEP alpha,
+    Hint(k) = the k-th out-of-domain value (trace arguments in air.trace_arguments() order, then the composition columns).
+    Same regrouping, so the patched program has the structure of the one compiled from values (alpha^0 folds to the literal 1
+    in both)."""
+    from .expr import Challenge, Hint
+
+    alpha = Challenge(0)
+    per_col: dict[int, Expr] = {}
+    k_off: dict[int, Expr] = {}
+    k = 0
+    for col, off in taps:
+        gi = Constant(pow(g, -off, p))
+        coeff = alpha.pow(k) * gi
+        term = coeff * Trace(u_col, -off)
+        per_col[col] = term if col not in per_col else per_col[col] + term
+        ky = coeff * Hint(k)
+        k_off[off] = ky if off not in k_off else k_off[off] + ky
+        k += 1
+    total = None
+    for col, a in per_col.items():
+        q = Trace(col, 0) * a
+        total = q if total is None else total + q
+    for off, kk in k_off.items():
+        q = kk * Trace(u_col, -off)
+        total = -q if total is None else total - q
+    comp, comp_y = None, None
+    for j in range(n_comp):
+        coeff = alpha.pow(k)
+        term = coeff * Trace(first_comp_col + j, 0)
+        comp = term if comp is None else comp + term
+        cy = coeff * Hint(k)
+        comp_y = cy if comp_y is None else comp_y + cy
+        k += 1
+    if comp is not None:
+        q = (comp - comp_y) * Trace(v_col, 0)
+        total = q if total is None else total + q
+    return total

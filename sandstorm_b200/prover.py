@@ -38,7 +38,7 @@ import torch
 from . import _lib
 from .air import compile_program, compile_template
 from .air.program import tap_reach
-from .air.deep import deep_expr_shifted, deep_terms
+from .air.deep import deep_expr_shifted, deep_expr_symbolic, deep_terms
 from .air.evaluate import evaluate
 from .air.expr import P
 from .air.layouts import load_layout
@@ -131,7 +131,7 @@ class HotPathProver:
         # columns of the working matrix: trace | composition (ce) | w = 1/(x-1) | u = 1/(x-z) | v = 1/(x-z^ce)
         C = self.layout.num_columns
         self.comp_col, self.w_col, self.u_col, self.v_col = C, C + self.ce, C + self.ce + 1, C + self.ce + 2
-        self._template = None
+        self._template = self._deep_template = None
         self._composition_program = None
         self._challenges = self._hints = self._alpha = None
         self.timeline: list = []
@@ -171,6 +171,21 @@ class HotPathProver:
             self._template = compile_template(L.composition(self.n, inv_x_minus_one_col=self.w_col), self.log_n, self.opt.log_blowup,
                                               L.n_challenges(), L.n_hints(), 1)
         return self._template
+
+    def deep_template(self):
+        """the DEEP quotient program (src/lib.rs:102-116 coefficients) with alpha and the out-of-domain values left open:
+        like the composition, only a value patch is left for the proof itself."""
+        if self._deep_template is None:
+            L = self.layout
+            taps = L.taps()
+            self._deep_template = compile_template(deep_expr_symbolic(taps, self.ce, self.comp_col, self.u_col, self.v_col, self.g, P), self.log_n,
+                                                   self.opt.log_blowup, 1, len(taps) + self.ce, 1)
+        return self._deep_template
+
+    def prepare(self):
+        """everything that depends only on (layout, trace length, options): call once, ahead of the proofs."""
+        self.composition_template()
+        self.deep_template()
 
     def composition_program(self, challenges, hints, alpha):
         """the per-proof value patch (a few milliseconds): constants <- challenges, hints, composition coefficient."""
@@ -334,12 +349,10 @@ class HotPathProver:
         coin.reseed_with_field_elements(res.ood_trace)
         coin.reseed_with_field_elements(res.ood_composition)
         alpha = res.deep_alpha = coin.draw()
-        t_terms, c_terms = deep_terms(taps, res.ood_trace, res.ood_composition, self.comp_col, alpha, P)
-        # (the sub-coset evaluation below reads u and v only at rows that are multiples of the blowup; launched first:
-        #  the GPU works while the host compiles)
+        # (the sub-coset evaluation below reads u and v only at rows that are multiples of the blowup)
         inv_x_minus_c(all_lde[self.u_col], _mont(z), c, log_row_step=b)
         inv_x_minus_c(all_lde[self.v_col], _mont(zc), c, log_row_step=b)
-        deep_prog = compile_program(deep_expr_shifted(t_terms, c_terms, self.u_col, self.v_col, self.g, P), self.log_n, b)
+        deep_prog = self.deep_template().patch([alpha], res.ood_trace + res.ood_composition, [0])
         del comp_coeffs, comp_evals, work
         # The quotient has degree < n - 1, so its n values on the sub-coset 3<w_n> — the LDE rows that are multiples of
         # the blowup — determine it: evaluate only those (1/blowup of the work), then extend like any other column
@@ -628,8 +641,7 @@ class HotPathProver:
         coin.reseed_with_field_elements(res.ood_trace)
         coin.reseed_with_field_elements(res.ood_composition)
         alpha = res.deep_alpha = coin.draw()
-        t_terms, c_terms = deep_terms(taps, res.ood_trace, res.ood_composition, self.comp_col, alpha, P)
-        deep_prog = compile_program(deep_expr_shifted(t_terms, c_terms, self.u_col, self.v_col, self.g, P), log_n, b)
+        deep_prog = self.deep_template().patch([alpha], res.ood_trace + res.ood_composition, [0])
         reach = tap_reach(deep_prog.blob, log_N)
         for col, point in ((self.u_col, z), (self.v_col, zc)):
             lo_t, hi_t = reach.get(col, (0, 0))

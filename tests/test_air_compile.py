@@ -211,3 +211,23 @@ def test_template_of_a_real_layout_matches_tree_evaluator():
     expr = L.composition(n)
     for i in (0, 1, 5, 2047, N - 3):
         assert run_blob(prog.blob, i, lde + [w_col], log_n + b) == eval_expr(expr, i, lde, log_n, b, ch, hints, alpha), i
+
+
+@pytest.mark.parametrize("name,log_n", [("plain", 7), ("recursive", 12), ("starknet", 16)])
+def test_deep_template_patch_is_the_direct_compilation(name, log_n):
+    """the DEEP quotient program compiled once with alpha and the out-of-domain values open, then patched, is byte for byte
+    the program compiled from the values (whose semantics test_deep_quotient_program_matches_definition pins)."""
+    import random
+
+    from sandstorm_b200.air import compile_template
+    from sandstorm_b200.air.deep import deep_expr_shifted, deep_expr_symbolic, deep_terms
+    from sandstorm_b200.air.layouts import load_layout
+
+    L = load_layout(name)
+    n, C, ce = 1 << log_n, L.num_columns, 2
+    g, taps, rnd = pow(3, (P - 1) // n, P), L.taps(), random.Random(log_n)
+    tpl = compile_template(deep_expr_symbolic(taps, ce, C, C + ce + 1, C + ce + 2, g, P), log_n, 1, 1, len(taps) + ce, 1)
+    for _ in range(2):
+        ood, oc, alpha = [rnd.randrange(P) for _ in taps], [rnd.randrange(P) for _ in range(ce)], rnd.randrange(P)
+        tt, ct = deep_terms(taps, ood, oc, C, alpha, P)
+        assert tpl.patch([alpha], ood + oc, [0]).blob == compile_program(deep_expr_shifted(tt, ct, C + ce + 1, C + ce + 2, g, P), log_n, 1).blob
