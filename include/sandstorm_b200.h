@@ -208,6 +208,25 @@ ss_status ss_ntt_shard(ss_ctx *ctx, ss_field field, const void *d_src, uint64_t 
 ss_status ss_shard_dft(ss_ctx *ctx, ss_field field, const void *d_in, uint64_t in_stride, void *d_out, uint64_t out_stride,
                        uint64_t count, int log_w, int inverse, int tw_log_m, uint64_t tw_offset, void *stream);
 
+/* Collectives of the row-sharded hot path over NCCL, one context per process / device (csrc/dist.cu; NCCL is bound at run time
+ * with dlopen, so single-GPU users need no NCCL).  Vectors and matrices are full-length device buffers of which this rank owns
+ * the block-cyclic pieces: rows [k m + r s, k m + (r+1) s), k < W, m = rows / W, s = m / W.
+ *   ss_dist_unique_id   rank 0 creates the 128-byte NCCL id; the host passes it to the other ranks by its own means
+ *   ss_dist_init        joins the communicator (collective); world = 2, 4 or 8
+ *   ss_dist_lde         one column: evaluations on <w_n> (src_on_coset: on 3<w_n>) -> evaluations on 3<w_N>, both block-cyclic
+ *   ss_dist_halo        the `halo` rows that follow every owned piece of every column, from the next rank (halo <= s)
+ *   ss_dist_commit      MatrixMerkleTree::from_matrix over all ranks' rows in bit-reversed leaf order -> root (collective, synchronises)
+ *   ss_dist_allgather   in-place all-gather of a block-cyclic vector */
+ss_status ss_dist_unique_id(ss_ctx *ctx, uint8_t id[128]);
+ss_status ss_dist_init(ss_ctx *ctx, const uint8_t id[128], int rank, int world);
+ss_status ss_dist_finalize(ss_ctx *ctx);
+ss_status ss_dist_lde(ss_ctx *ctx, ss_field field, const void *d_src, int log_n, int log_blowup, int src_on_coset, void *d_dst,
+                      void *stream);
+ss_status ss_dist_halo(ss_ctx *ctx, void *d_cols, uint64_t col_stride, int n_cols, int log_rows, uint64_t halo, void *stream);
+ss_status ss_dist_allgather(ss_ctx *ctx, void *d_vec, int log_rows, void *stream);
+ss_status ss_dist_commit(ss_ctx *ctx, ss_tree_kind kind, int n_friendly, const void *d_cols, uint64_t col_stride, int n_cols,
+                         int log_rows, uint8_t root[32], void *stream);
+
 /* ------------------------------------------------------------------ extension columns (§8 f1)
  * Trace::build_extension_columns (layouts/src/recursive/trace.rs:699-814, starknet/trace.rs:997-1100) as device prefix
  * scans instead of the reference's sequential loops + batch_inversion.  Elements are read at index j * stride of the

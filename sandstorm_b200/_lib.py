@@ -55,6 +55,13 @@ SIGNATURES = {
     "ss_pow_grind": (c_int, [c_void_p, c_int, POINTER(c_uint8), c_int, POINTER(c_uint64)]),
     "ss_ntt_shard": (c_int, [c_void_p, c_int, c_void_p, c_uint64, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_uint64, c_void_p]),
     "ss_shard_dft": (c_int, [c_void_p, c_int, c_void_p, c_uint64, c_void_p, c_uint64, c_uint64, c_int, c_int, c_int, c_uint64, c_void_p]),
+    "ss_dist_unique_id": (c_int, [c_void_p, POINTER(c_uint8)]),
+    "ss_dist_init": (c_int, [c_void_p, POINTER(c_uint8), c_int, c_int]),
+    "ss_dist_finalize": (c_int, [c_void_p]),
+    "ss_dist_lde": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "ss_dist_halo": (c_int, [c_void_p, c_void_p, c_uint64, c_int, c_int, c_uint64, c_void_p]),
+    "ss_dist_allgather": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "ss_dist_commit": (c_int, [c_void_p, c_int, c_int, c_void_p, c_uint64, c_int, c_int, POINTER(c_uint8), c_void_p]),
     "ss_perm_product": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_uint64, c_uint64, c_void_p, c_void_p, c_void_p, c_uint64, c_void_p]),
     "ss_diluted_aggregate": (c_int, [c_void_p, c_int, c_void_p, c_uint64, c_uint64, c_void_p, c_void_p, c_void_p, c_uint64, c_void_p]),
     "ss_constraint_eval": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_uint64, c_int, c_int, c_int, c_uint64, c_uint64, c_int, c_void_p, c_void_p]),

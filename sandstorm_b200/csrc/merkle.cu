@@ -192,6 +192,51 @@ __global__ void __launch_bounds__(256) node_levels_fused_kernel(const uint8_t *c
     }
 }
 
+// Three levels per launch with every thread busy: a thread owns 8 consecutive children (256 contiguous bytes) and computes
+// the 4 + 2 + 1 nodes above them one after the other, in registers.  Same hash count as level-by-level launches (the levels
+// are compute-bound), a third of the launches and no re-read of the two intermediate levels.
+template <int BH>
+__global__ void __launch_bounds__(128) node_levels3_kernel(const uint8_t *children, int dc, unsigned long long count, int mask, uint8_t *nodes) {
+    const unsigned long long t = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;     // node index at depth dc - 3
+    if (t >= count) return;
+    const uint4 *src = reinterpret_cast<const uint4 *>(children) + 16ull * t;
+    auto put = [&](int depth, unsigned long long j, const uint32_t (&d)[8]) {
+        uint4 *dst = reinterpret_cast<uint4 *>(nodes + 32ull * ((1ull << depth) + j));
+        dst[0] = make_uint4(d[0], d[1], d[2], d[3]);
+        dst[1] = make_uint4(d[4], d[5], d[6], d[7]);
+    };
+    auto masked = [&](uint32_t (&d)[8]) {
+        if (mask == MASK_KEEP_FIRST20) { d[5] = 0; d[6] = 0; d[7] = 0; }
+        if (mask == MASK_KEEP_LAST20) { d[0] = 0; d[1] = 0; d[2] = 0; }
+    };
+    uint32_t top[16];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {                       // the two halves of 4 children each
+        uint32_t mid[16];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {                   // a pair of children -> one node of depth dc - 1
+            uint32_t c[16], d[8];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const uint4 v = __ldg(src + 8 * h + 4 * q + k); c[4 * k] = v.x; c[4 * k + 1] = v.y; c[4 * k + 2] = v.z; c[4 * k + 3] = v.w; }
+            node_digest<BH>(c, d);
+            masked(d);
+            put(dc - 1, 4 * t + 2 * h + q, d);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mid[8 * q + k] = d[k];
+        }
+        uint32_t d[8];
+        node_digest<BH>(mid, d);
+        masked(d);
+        put(dc - 2, 2 * t + h, d);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) top[8 * h + k] = d[k];
+    }
+    uint32_t d[8];
+    node_digest<BH>(top, d);
+    masked(d);
+    put(dc - 3, t, d);
+}
+
 __device__ __forceinline__ Fp load_fp(const uint8_t *p) {
     const uint4 *q = reinterpret_cast<const uint4 *>(p);
     const uint4 a = __ldg(q), b = __ldg(q + 1);
@@ -320,16 +365,25 @@ void build_node_levels(ss_ctx *ctx, ss_tree *t, int bh, int mask, const Pedersen
     while (d >= 0) {
         const uint8_t *children = (d == height - 1) ? t->d_leaves : t->d_nodes + 64ull * (1ull << d);
         if (d >= transition) {
-            int levels = d - transition + 1;              // byte-hash levels left
-            if (levels > FUSED_LEVELS) levels = FUSED_LEVELS;
-            if (levels >= 2 && ss::option(ctx, "merkle_fused", 1)) {
-                const unsigned grid = (unsigned)(1ull << (d + 1 - levels));
+            const int left = d - transition + 1;          // byte-hash levels left
+            const bool fused = ss::option(ctx, "merkle_fused", 1) != 0;
+            if (fused && d + 1 <= FUSED_LEVELS && left >= 2) {
+                // the top of the tree: one CTA walks all remaining levels in shared memory instead of one tiny launch each
+                const int levels = left;
                 by_byte_hash(bh, [&](auto BH) {
-                    node_levels_fused_kernel<decltype(BH)::value><<<grid, 256, 0, st>>>(children, d + 1, levels, mask, t->d_nodes);
+                    node_levels_fused_kernel<decltype(BH)::value><<<1u << (d + 1 - levels), 256, 0, st>>>(children, d + 1, levels, mask, t->d_nodes);
                     ctx->launches++;
                     return SS_OK;
                 });
                 d -= levels;
+            } else if (fused && left >= 3 && d >= 2) {
+                const unsigned long long c = 1ull << (d - 2);                  // nodes at depth d - 2
+                by_byte_hash(bh, [&](auto BH) {
+                    node_levels3_kernel<decltype(BH)::value><<<grid_for(c, 128), 128, 0, st>>>(children, d + 1, c, mask, t->d_nodes);
+                    ctx->launches++;
+                    return SS_OK;
+                });
+                d -= 3;
             } else {
                 const unsigned long long c = 1ull << d;
                 by_byte_hash(bh, [&](auto BH) {

@@ -65,6 +65,8 @@ class ProofOptions:
     max_remainder_coeffs: int = 16
     grinding_factor: int = 0                     # cli default 16 (cli/src/main.rs:55); 0 skips the search
     ce_blowup: int = 2                           # composition columns (src/lib.rs:110-113 air.ce_blowup_factor())
+    capi_collectives: bool = False               # world > 1: LDE / halo / commit / all-gather through the C ABI's own NCCL calls
+                                                 # (csrc/dist.cu: what a Rust host uses) instead of torch.distributed
     tree_kind: int = _lib.TREE_KECCAK_M20        # src/claims.rs:18-21 (starknet / EthVerifier); recursive claims use TREE_FRIENDLY
     n_friendly: int = 22                         # NUM_FRIENDLY_COMMITMENT_LAYERS, src/claims.rs:10 (TREE_FRIENDLY only)
     col_pad_rows: int = 0                        # padding between the columns of the working matrix (not a protocol parameter)
@@ -547,24 +549,57 @@ class HotPathProver:
             raise ValueError("trace too short to shard over this many GPUs")
         st = ShardedTransforms(rank, W, DeviceShardOps(c), dev)
         PN, Pn = pieces(log_N, rank, W), pieces(log_n, rank, W)
+        halo = L.max_offset << b
+        capi = opt.capi_collectives
+        if capi and not getattr(c, "_dist_ready", False):
+            ident = (ctypes.c_uint8 * 128)()
+            if rank == 0:
+                c.check(c.lib.ss_dist_unique_id(c.handle, ident))
+            t = torch.tensor(list(ident), dtype=torch.uint8, device=dev)
+            dist.broadcast(t, 0)                                            # (the id travels by the host's own means)
+            ident = (ctypes.c_uint8 * 128)(*t.cpu().tolist())
+            c.check(c.lib.ss_dist_init(c.handle, ident, rank, W))
+            c._dist_ready = True
+        from .matrix import _stream_ptr
+
+        def lde_one(src_col, dst_col, on_coset=False):
+            if capi:
+                c.check(c.lib.ss_dist_lde(c.handle, _lib.FIELD_FP252, ctypes.c_void_p(src_col.data_ptr()), log_n, b, int(on_coset),
+                                          ctypes.c_void_p(dst_col.data_ptr()), _stream_ptr()))
+            else:
+                st.lde(src_col, log_n, b, dst_col, src_on_coset=on_coset)
+
+        def halo_of(cols):
+            if capi and halo and halo <= PN[0][1]:
+                c.check(c.lib.ss_dist_halo(c.handle, ctypes.c_void_p(cols.data_ptr()), S, cols.shape[0], log_N, halo, _stream_ptr()))
+            else:
+                self._exchange_halo(cols, log_N, halo)
+
+        def commit(cols):
+            if capi:
+                root = (ctypes.c_uint8 * 32)()
+                c.check(c.lib.ss_dist_commit(c.handle, opt.tree_kind, opt.n_friendly, ctypes.c_void_p(cols.data_ptr()), S, cols.shape[0], log_N,
+                                             root, _stream_ptr()))
+                return bytes(root)
+            return self._commit_pieces(cols, S, log_N)
+
         self.mark("start")
         S = N + opt.col_pad_rows
         all_lde = torch.empty((C + self.ce + 3, S, 4), dtype=torch.int64, device=dev)[:, :N]
         lde = all_lde[:C]
-        halo = L.max_offset << b
 
         def lde_cols(src: Matrix, first_col: int):
             for j in range(src.num_cols):
                 if column_ready is not None:
                     column_ready(first_col + j)
-                st.lde(src.data[j], log_n, b, lde[first_col + j])
+                lde_one(src.data[j], lde[first_col + j])
 
         # 3-5: base trace
         lde_cols(base, 0)
         self.mark("lde_base")
-        self._exchange_halo(lde[:nb], log_N, halo)
+        halo_of(lde[:nb])
         self.mark("share_base")
-        res.roots["base"] = self._commit_pieces(lde[:nb], S, log_N)
+        res.roots["base"] = commit(lde[:nb])
         self.mark("merkle_base")
         coin.reseed_with_digest(res.roots["base"])
         challenges = res.challenges = [coin.draw() for _ in range(L.n_challenges())]
@@ -579,9 +614,9 @@ class HotPathProver:
         # 8: extension trace
         lde_cols(ext, nb)
         self.mark("lde_ext")
-        self._exchange_halo(lde[nb:], log_N, halo)
+        halo_of(lde[nb:C])
         self.mark("share_ext")
-        res.roots["ext"] = self._commit_pieces(lde[nb:C], S, log_N)
+        res.roots["ext"] = commit(lde[nb:C])
         self.mark("merkle_ext")
         coin.reseed_with_digest(res.roots["ext"])
         # 9: constraint evaluation on the owned pieces
@@ -605,7 +640,7 @@ class HotPathProver:
         comp_lde = all_lde[self.comp_col:self.comp_col + self.ce]
         shares = st.composition_columns(comp_evals, log_n, b, [comp_lde[0], comp_lde[1]])
         self.mark("ntt_comp")
-        res.roots["composition"] = self._commit_pieces(comp_lde, S, log_N)
+        res.roots["composition"] = commit(comp_lde)
         self.mark("merkle_comp")
         # 11: out-of-domain values: partial barycentric sums over the owned trace rows, summed over the ranks
         coin.reseed_with_digest(res.roots["composition"])
@@ -656,8 +691,11 @@ class HotPathProver:
         for lo, cnt in PN:
             evaluate(deep_prog, Matrix(all_lde, c), b, out=quotient, rows=(lo, cnt >> b), log_row_step=b)
         self.mark("deep")
-        st.lde(quotient, log_n, b, deep, src_on_coset=True)
-        self._gather_pieces(deep, log_N)
+        lde_one(quotient, deep, on_coset=True)
+        if capi:
+            c.check(c.lib.ss_dist_allgather(c.handle, ctypes.c_void_p(deep.data_ptr()), log_N, _stream_ptr()))
+        else:
+            self._gather_pieces(deep, log_N)
         self.mark("deep_lde")
         del comp_evals, quotient
         # 13: FRI layers on the gathered evaluations (tree-leaf / row ranges per rank while the layers are large)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Multi-GPU parity check (run under torchrun, one process per GPU): the sharded hot path (world > 1) must produce
 the same commitments, out-of-domain values, FRI roots and remainder as the single-GPU path on the same seeded trace.
-    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/check_multi_gpu.py [layout] [log_n] [keccak_m20|friendly]"""
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/check_multi_gpu.py [layout] [log_n] [keccak_m20|friendly] [capi]"""
 import os
 import sys
 
@@ -19,6 +19,7 @@ def main():
     log_n = int(sys.argv[2]) if len(sys.argv) > 2 else 18
     tree = sys.argv[3] if len(sys.argv) > 3 else "keccak_m20"
     kind = ss.TREE_FRIENDLY if tree == "friendly" else ss.TREE_KECCAK_M20
+    capi = len(sys.argv) > 4 and sys.argv[4] == "capi"            # collectives through csrc/dist.cu instead of torch.distributed
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -30,7 +31,7 @@ def main():
         t[:, :, 3] &= (1 << 58) - 1
         return t
 
-    sharded = HotPathProver(layout, log_n, ProofOptions(tree_kind=kind), rank=rank, world=world)
+    sharded = HotPathProver(layout, log_n, ProofOptions(tree_kind=kind, capi_collectives=capi), rank=rank, world=world)
     L = sharded.layout
     base, ext = rand_cols(L.num_base_columns, 1 << log_n), rand_cols(L.num_extension_columns, 1 << log_n)
     got = sharded.prove(ss.Matrix(base), ss.Matrix(ext), queries=False)
@@ -43,7 +44,7 @@ def main():
         checks = {"roots": got.roots == want.roots, "fri_roots": got.fri_roots == want.fri_roots, "ood_trace": got.ood_trace == want.ood_trace,
                   "ood_composition": got.ood_composition == want.ood_composition, "remainder": np.array_equal(got.remainder, want.remainder)}
         ok = all(checks.values())
-        print({"layout": layout, "log_n": log_n, "world": world, **checks, "ok": ok}, flush=True)
+        print({"layout": layout, "log_n": log_n, "world": world, "capi": capi, **checks, "ok": ok}, flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
