@@ -376,8 +376,21 @@ def gpu_arm(args):
         dev_col = lambda k: hp.base[k] if k < hp.n_base else hp.ext[k - hp.n_base]
         # what this rank uploads of EVERY column: all rows on one GPU, its block-cyclic pieces (+ the OOD reach) on several
         ranges = hp.prover.trace_rows_needed()
-        plan = [[(dev_col(k)[a:a + cnt], dev_col(k)[a:a + cnt].cpu().pin_memory()) for a, cnt in ranges] for k in range(n_trace_cols)]
-        my_h2d = sum(h.numel() * 8 for col in plan for _, h in col)
+        # host side through the C ABI, as the Rust host would do it: the trace lives in ordinary host arrays that are pinned
+        # once with ss_host_register (ministark's GpuVec columns) and uploaded with ss_memcpy_h2d on the copy stream
+        import ctypes
+
+        lib, h = ctx.lib, ctx.handle
+        plan = []
+        for k in range(n_trace_cols):
+            parts = []
+            for a, cnt in ranges:
+                dst = dev_col(k)[a:a + cnt]
+                host = dst.cpu().numpy()
+                ctx.check(lib.ss_host_register(h, ctypes.c_void_p(host.ctypes.data), host.nbytes))
+                parts.append((dst, host))
+            plan.append(parts)
+        my_h2d = sum(host.nbytes for col in plan for _, host in col)
 
         def e2e_step():
             # the trace is uploaded column by column on a copy stream; the LDE of column k waits only for column k,
@@ -385,13 +398,13 @@ def gpu_arm(args):
             main = torch.cuda.current_stream()
             copy_stream.wait_stream(main)                  # the previous step has finished reading the buffers
             events = []
-            with torch.cuda.stream(copy_stream):
-                for k in range(n_trace_cols):
-                    for dst, src in plan[k]:
-                        dst.copy_(src, non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(copy_stream)
-                    events.append(ev)
+            for k in range(n_trace_cols):
+                for dst, host in plan[k]:
+                    ctx.check(lib.ss_memcpy_h2d(h, ctypes.c_void_p(dst.data_ptr()), ctypes.c_void_p(host.ctypes.data), host.nbytes,
+                                                ctypes.c_void_p(copy_stream.cuda_stream)))
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                events.append(ev)
             hp.column_ready = lambda k: main.wait_stream(copy_stream) if k is None else main.wait_event(events[k])
             hp.step()                                      # reads its roots, OOD values, remainder and openings back itself (D2H)
             main.wait_stream(copy_stream)
@@ -420,6 +433,9 @@ def gpu_arm(args):
                "ms_per_step": e2e_ms, "prove_seconds": e2e_ms / 1e3,
                "note": "the step's NTT field-ops over the WHOLE step incl. copies (every stage in the denominator).  The uploads run on a copy "
                        "stream under the first LDE stage, so this can land within run-to-run noise of the device-resident step."}
+        for col in plan:
+            for _, host in col:
+                lib.ss_host_unregister(h, ctypes.c_void_p(host.ctypes.data))
         del plan
 
     # ---- the 2^24-point NTT the north_star roofline target is quoted on (8 columns, forward + inverse) ----------------

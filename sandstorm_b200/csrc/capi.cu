@@ -121,8 +121,11 @@ void ss_destroy(ss_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    for (ss_tree *t : ctx->live_trees)
+        if (ctx->detach_tree) ctx->detach_tree(t);            // their blocks are freed with the pool below
+    ctx->live_trees.clear();
     dev_trim(ctx);
-    for (auto &kv : ctx->pool_size) cudaFree(kv.first);       // blocks still held by live trees die with the context
+    for (auto &kv : ctx->pool_size) cudaFree(kv.first);       // blocks still held by (now detached) trees die with the context
     for (auto &kv : ctx->tables) cudaFree(kv.second);
     for (auto &kv : ctx->scale_tables) { cudaFree(kv.second.first); cudaFree(kv.second.second); }
     if (ctx->scratch) cudaFree(ctx->scratch);

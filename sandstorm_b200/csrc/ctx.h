@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <map>
+#include <set>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -25,6 +26,10 @@ struct ss_ctx {
     // device blocks released by dev_free, kept for reuse (size -> pointers) and the size of every live block
     std::multimap<size_t, void *> pool_free;
     std::map<void *, size_t> pool_size;
+    // trees built through this context and not yet freed: ss_destroy releases their device memory and detaches them, so a
+    // later ss_tree_free of such a tree only deletes the handle instead of touching a dead context
+    std::set<struct ss_tree *> live_trees;
+    void (*detach_tree)(struct ss_tree *) = nullptr;
     // geometric scale tables c * h^k of the sharded transforms, keyed by (log length, c, h) (ntt_host.cu custom_scale)
     std::map<std::vector<uint32_t>, std::pair<void *, void *>> scale_tables;
     // pinned staging area for small host -> device uploads that must not block the caller (program blobs)

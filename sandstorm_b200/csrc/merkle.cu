@@ -273,32 +273,49 @@ __device__ __forceinline__ AffinePt load_pt(const AffinePt *p) {
 //         = H(H(H(0, l0), l1), 2)   (crypto/src/hash/pedersen.rs:67-76; single-column first level)
 __global__ void __launch_bounds__(128) pedersen_node_kernel(const uint8_t *children, unsigned long long count, int mode,
                                                               PedersenTable tab, uint8_t *out) {
+    __shared__ Fp inv_sm[256];
     const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    const uint8_t *c = children + 64ull * i;
-    Fp a, b;
-    if (mode == 1) { a = digest_to_felt(c); b = digest_to_felt(c + 32); }
-    else { a = load_fp(c); b = load_fp(c + 32); }
+    const bool on = i < count;                                   // (every thread takes part in the block-wide inversions)
+    Fp a = fp::zero(), b = fp::zero();
+    if (on) {
+        const uint8_t *c = children + 64ull * i;
+        if (mode == 1) { a = digest_to_felt(c); b = digest_to_felt(c + 32); }
+        else { a = load_fp(c); b = load_fp(c + 32); }
+    }
     const AffinePt p0 = load_pt(tab.pts + ec::PED_TABLE_POINTS);
     auto ld = [&](int idx) { return load_pt(tab.pts + idx); };
+    // x = X / Z^2 with the Z's of the block inverted together
+    auto hash = [&](const Fp &u, const Fp &v) {
+        JacPt s;
+        s.x = fp::one(); s.z = fp::one();
+        if (on) s = ec::pedersen_sum(u, v, p0, ld);
+        if (ec::is_zero_mod_p(s.z)) s.z = fp::one();             // infinity (no valid input gives it): keep the block's product invertible
+        const Fp zi = ec::block_inverse<128>(s.z, inv_sm);
+        return fp::canon(fp::mul(s.x, fp::sqr(zi)));
+    };
     Fp h;
     if (mode == 2) {
-        h = ec::pedersen_hash(fp::zero(), a, p0, ld);
-        h = ec::pedersen_hash(h, b, p0, ld);
-        h = ec::pedersen_hash(h, fp::from_u32(2), p0, ld);
+        h = hash(fp::zero(), a);
+        h = hash(h, b);
+        h = hash(h, fp::from_u32(2));
     } else {
-        h = ec::pedersen_hash(a, b, p0, ld);
+        h = hash(a, b);
     }
-    store_fp(out + 32ull * i, h);
+    if (on) store_fp(out + 32ull * i, h);
 }
 
-__global__ void pedersen_batch_kernel(const Fp *a, const Fp *b, Fp *out, unsigned long long count, PedersenTable tab) {
+__global__ void __launch_bounds__(128) pedersen_batch_kernel(const Fp *a, const Fp *b, Fp *out, unsigned long long count, PedersenTable tab) {
+    __shared__ Fp inv_sm[256];
     const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-    if (i >= count) return;
+    const bool on = i < count;
     const AffinePt p0 = load_pt(tab.pts + ec::PED_TABLE_POINTS);
     auto ld = [&](int idx) { return load_pt(tab.pts + idx); };
-    const Fp h = ec::pedersen_hash(load_fp(reinterpret_cast<const uint8_t *>(a + i)), load_fp(reinterpret_cast<const uint8_t *>(b + i)), p0, ld);
-    store_fp(reinterpret_cast<uint8_t *>(out + i), h);
+    JacPt s;
+    s.x = fp::one(); s.z = fp::one();
+    if (on) s = ec::pedersen_sum(load_fp(reinterpret_cast<const uint8_t *>(a + i)), load_fp(reinterpret_cast<const uint8_t *>(b + i)), p0, ld);
+    if (ec::is_zero_mod_p(s.z)) s.z = fp::one();
+    const Fp zi = ec::block_inverse<128>(s.z, inv_sm);
+    if (on) store_fp(reinterpret_cast<uint8_t *>(out + i), fp::canon(fp::mul(s.x, fp::sqr(zi))));
 }
 
 __global__ void copy_column_kernel(const Fp *col, int log_rows, int bitrev, uint8_t *out) {
@@ -355,6 +372,11 @@ void byte_hash_of(int kind, int &bh, int &mask) {
     case SS_TREE_FRIENDLY: case SS_TREE_BLAKE2S_M20: bh = BH_BLAKE2S; mask = MASK_KEEP_LAST20; break;
     default: bh = BH_SHA256; mask = MASK_NONE; break;
     }
+}
+
+void register_tree(ss_ctx *ctx, ss_tree *t) {
+    ctx->live_trees.insert(t);
+    ctx->detach_tree = [](ss_tree *tree) { tree->ctx = nullptr; tree->d_leaves = nullptr; tree->d_nodes = nullptr; };
 }
 
 // node levels above row digests (n_cols >= 2 trees): byte-hash levels FUSED_LEVELS at a time, Pedersen levels one by one
@@ -485,6 +507,7 @@ ss_status ss_merkle_build(ss_ctx *ctx, ss_tree_kind kind, int n_friendly, const 
         return fail(ctx, SS_ERR_CUDA, "ss_merkle_build: launch failed: %s", cudaGetErrorString(e));
     }
     (void)rc;
+    register_tree(ctx, t);
     *out = t;
     return SS_OK;
 }
@@ -545,6 +568,7 @@ ss_status ss_merkle_build_from_leaves(ss_ctx *ctx, ss_tree_kind kind, int n_frie
         dev_free(ctx, t->d_leaves); dev_free(ctx, t->d_nodes); delete t;
         return fail(ctx, SS_ERR_CUDA, "ss_merkle_build_from_leaves: launch failed: %s", cudaGetErrorString(e));
     }
+    register_tree(ctx, t);
     *out = t;
     return SS_OK;
 }
@@ -691,6 +715,8 @@ int ss_tree_log_rows(const ss_tree *tree) { return tree ? tree->log_rows : -1; }
 
 void ss_tree_free(ss_tree *tree) {
     if (!tree) return;
+    if (!tree->ctx) { delete tree; return; }                 // the context was destroyed first: its memory is already gone
+    tree->ctx->live_trees.erase(tree);
     cudaSetDevice(tree->ctx->device);
     dev_free(tree->ctx, tree->d_leaves);
     dev_free(tree->ctx, tree->d_nodes);

@@ -84,6 +84,57 @@ SS_HD Fp inv_chain(const Fp &x) {
 SS_HD uint32_t ped_digit(const Fp &c, int w) { return (c.l[w >> 2] >> ((w & 3) * 8)) & 0xffu; }
 SS_HD uint32_t ped_high(const Fp &c) { return (c.l[7] >> 24) & 0xfu; }
 
+// The sum P0 + a_lo P1 + a_hi P2 + b_lo P3 + b_hi P4 in Jacobian coordinates: the hash is X / Z^2.  Callers that hash many
+// pairs at once invert the Z's together (one inversion per thread block: Montgomery's trick, block_inverse below) instead
+// of paying a 250-squaring Fermat chain per hash — a quarter of the multiplications of a hash.
+template <typename LoadPt>
+SS_HD JacPt pedersen_sum(const Fp &a_mont, const Fp &b_mont, const AffinePt &p0, LoadPt load_pt) {
+    JacPt acc; acc.x = p0.x; acc.y = p0.y; acc.z = fp::one();
+    Fp one_int = fp::zero(); one_int.l[0] = 1;
+#pragma unroll 1
+    for (int e = 0; e < 2; ++e) {
+        const Fp c = fp::canon(fp::mul(e == 0 ? a_mont : b_mont, one_int));
+        const int base = e * PED_POINTS_PER_INPUT;
+#pragma unroll 1
+        for (int w = 0; w < PED_LOW_WINDOWS; ++w) {
+            const uint32_t d = ped_digit(c, w);
+            if (d) acc = jac_add_affine(acc, load_pt(base + w * PED_DIGITS + (int)d - 1));
+        }
+        const uint32_t hi = ped_high(c);
+        if (hi) acc = jac_add_affine(acc, load_pt(base + PED_LOW_WINDOWS * PED_DIGITS + (int)hi - 1));
+    }
+    return acc;
+}
+
+#ifdef __CUDACC__
+// Inverse of every thread's value with ONE field inversion per block: up-sweep of pairwise products in shared memory,
+// thread 0 inverts the root, down-sweep.  Every thread of the block must call it; sm holds 2 * THREADS elements.
+template <int THREADS>
+__device__ __forceinline__ Fp block_inverse(const Fp &v, Fp *sm) {
+    const int tid = threadIdx.x;
+    sm[THREADS + tid] = v;
+    __syncthreads();
+    for (int w = THREADS / 2; w >= 1; w >>= 1) {
+        if (tid < w) sm[w + tid] = fp::mul(sm[2 * (w + tid)], sm[2 * (w + tid) + 1]);
+        __syncthreads();
+    }
+    if (tid == 0) sm[1] = inv_chain(sm[1]);
+    __syncthreads();
+    for (int w = 1; w < THREADS; w <<= 1) {
+        if (tid < w) {
+            const int k = w + tid;
+            const Fp ik = sm[k], l = sm[2 * k], r = sm[2 * k + 1];
+            sm[2 * k] = fp::mul(ik, r);
+            sm[2 * k + 1] = fp::mul(ik, l);
+        }
+        __syncthreads();
+    }
+    const Fp out = sm[THREADS + tid];
+    __syncthreads();                                   // sm may be reused by the next call
+    return out;
+}
+#endif
+
 // Montgomery-form inputs/outputs.  `table` as laid out above, `p0` = shift point.
 template <typename LoadPt>
 SS_HD Fp pedersen_hash(const Fp &a_mont, const Fp &b_mont, const AffinePt &p0, LoadPt load_pt) {

@@ -256,20 +256,31 @@ class ShardedTransforms:
     # ---- LDE of one column: block-cyclic evaluations on <w_n> (or 3<w_n>) -> block-cyclic evaluations on 3<w_N> ---------
     def lde(self, src: torch.Tensor, log_n: int, log_blowup: int, dst: torch.Tensor, src_on_coset: bool = False) -> None:
         """src on <w_n> (trace columns) or, with src_on_coset, on 3<w_n> (the DEEP quotient); dst on 3<w_N>."""
+        self.lde_begin(src, log_n)
+        self.lde_finish(log_n, log_blowup, dst, src_on_coset)
+
+    def lde_begin(self, src: torch.Tensor, log_n: int, slot: int = 0) -> None:
+        """first half: the size-W transform of the owned rows and the first all-to-all (into this slot's buffers)."""
+        W, r = self.world, self.rank
+        m = (1 << log_n) // W
+        s = m // W
+        send, recv = self._tmp(f"send{slot}", m), self._tmp(f"recv{slot}", m)
+        self.ops.dft(src, r * s, m, send, 0, s, s, self.log_w, True, log_n, r * s)
+        _all_to_all(recv.view(W, s, 4), send.view(W, s, 4), W)
+
+    def lde_finish(self, log_n: int, log_blowup: int, dst: torch.Tensor, src_on_coset: bool = False, slot: int = 0) -> None:
+        """second half: the local LDE, the second all-to-all and the size-W transform into the owned pieces of dst."""
         W, r = self.world, self.rank
         n = 1 << log_n
         m = n // W
-        s = m // W
         ninv = pow(n, -1, P252)
         c0, h0 = (ninv, 1) if src_on_coset else (ninv * pow(GEN, r, P252) % P252, pow(GEN, W, P252))
-        send, recv = self._tmp("send", m), self._tmp("recv", m)
-        self.ops.dft(src, r * s, m, send, 0, s, s, self.log_w, True, log_n, r * s)
-        _all_to_all(recv.view(W, s, 4), send.view(W, s, 4), W)
+        recv = self._tmp(f"recv{slot}", m)
         mN = m << log_blowup
         sN = mN // W
-        z = self._tmp("z", mN)
+        z = self._tmp(f"z{slot}", mN)
         self.ops.ntt_shard(recv, m.bit_length() - 1, 3, log_blowup, c0, h0, self._twiddle(log_n + log_blowup), z)
-        recv2 = self._tmp("recv2", mN)
+        recv2 = self._tmp(f"recv2{slot}", mN)
         _all_to_all(recv2.view(W, sN, 4), z.view(W, sN, 4), W)
         self.ops.dft(recv2, 0, sN, dst, r * sN, mN, sN, self.log_w, False, -1, 0)
 

@@ -487,6 +487,16 @@ class HotPathProver:
         c.check(c.lib.ss_merkle_combine(c.handle, opt.tree_kind, buf, log_w, root))
         return bytes(root)
 
+    def _lde_pipes(self, dev, W, rank):
+        """two (stream, ShardedTransforms) pairs, each with its own context (scratch buffers and work-buffer pool are per context
+        and recycled in stream order)."""
+        if getattr(self, "_pipes", None) is None:
+            from .context import Context
+            from .parallel import DeviceShardOps, ShardedTransforms
+
+            self._pipes = [(torch.cuda.Stream(), ShardedTransforms(rank, W, DeviceShardOps(Context(dev.index)), dev)) for _ in range(2)]
+        return self._pipes
+
     def _gather_pieces(self, vec: torch.Tensor, log_len: int) -> None:
         """all-gather of a block-cyclic vector, in place: afterwards every rank holds every row."""
         import torch.distributed as dist
@@ -589,10 +599,37 @@ class HotPathProver:
         lde = all_lde[:C]
 
         def lde_cols(src: Matrix, first_col: int):
-            for j in range(src.num_cols):
+            k = src.num_cols
+            if capi or k == 1:
+                for j in range(k):
+                    if column_ready is not None:
+                        column_ready(first_col + j)
+                    lde_one(src.data[j], lde[first_col + j])
+                return
+            # software pipeline over the columns: while the local LDE of column j runs on one stream, the first exchange of
+            # column j + 1 and the second exchange of column j - 1 proceed on the other (two contexts: separate scratch)
+            main = torch.cuda.current_stream()
+            pipes = self._lde_pipes(dev, W, rank)
+            for stream, _ in pipes:
+                stream.wait_stream(main)
+
+            def begin(j):
                 if column_ready is not None:
                     column_ready(first_col + j)
-                lde_one(src.data[j], lde[first_col + j])
+                stream, stx = pipes[j & 1]
+                stream.wait_stream(main)                 # (column_ready made `main` wait for the column's upload)
+                with torch.cuda.stream(stream):
+                    stx.lde_begin(src.data[j], log_n, slot=j & 1)
+
+            begin(0)
+            for j in range(k):
+                if j + 1 < k:
+                    begin(j + 1)
+                stream, stx = pipes[j & 1]
+                with torch.cuda.stream(stream):
+                    stx.lde_finish(log_n, b, lde[first_col + j], slot=j & 1)
+            for stream, _ in pipes:
+                main.wait_stream(stream)
 
         # 3-5: base trace
         lde_cols(base, 0)

@@ -127,3 +127,29 @@ def test_large_roundtrip_and_sampled_rows(ss, oracle, log_n):
         assert np.array_equal(f.numpy()[0], want_small[0])
     del f, m
     torch.cuda.empty_cache()
+
+
+def test_registered_host_columns_upload_through_the_abi(ss, oracle):
+    """ss_host_register + ss_memcpy_h2d (the GpuVec / GpuAllocator role, layouts/src/recursive/trace.rs:55-56): an ordinary host
+    array is pinned in place, uploaded asynchronously on a side stream and transformed; bench.py's e2e leg moves the trace this way."""
+    import ctypes
+
+    import torch
+
+    rng = np.random.default_rng(9)
+    cols = oracle.random_felts(rng, 2, 1 << 10)
+    host = np.ascontiguousarray(cols)
+    dev = torch.empty((2, 1 << 10, 4), dtype=torch.int64, device="cuda")
+    c = ss.default_context()
+    side = torch.cuda.Stream()
+    c.check(c.lib.ss_host_register(c.handle, ctypes.c_void_p(host.ctypes.data), host.nbytes))
+    try:
+        c.check(c.lib.ss_memcpy_h2d(c.handle, ctypes.c_void_p(dev.data_ptr()), ctypes.c_void_p(host.ctypes.data), host.nbytes, ctypes.c_void_p(side.cuda_stream)))
+        torch.cuda.current_stream().wait_stream(side)
+        lde = ss.Matrix(dev).lde(1)
+        back = np.zeros_like(host)
+        c.check(c.lib.ss_memcpy_d2h(c.handle, ctypes.c_void_p(back.ctypes.data), ctypes.c_void_p(dev.data_ptr()), host.nbytes, None))
+        torch.cuda.synchronize()
+    finally:
+        c.check(c.lib.ss_host_unregister(c.handle, ctypes.c_void_p(host.ctypes.data)))
+    assert np.array_equal(back, cols) and np.array_equal(lde.numpy(), oracle.lde(cols, 1))
