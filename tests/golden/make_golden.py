@@ -52,3 +52,25 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def poseidon_params():
+    """poseidon_params.json — round keys of the Poseidon builtin (builtins/src/poseidon/params.rs:21-483, :520-604), inputs of the
+    restated starknet trace builder (oracle/cairo.py); the MDS matrix [[3,1,1],[1,-1,1],[1,1,-2]] (:15-19) is written out there."""
+    src = open(os.path.join(REF, "builtins/src/poseidon/params.rs")).read()
+    out = {}
+    m = re.search(r"pub const PARTIAL_ROUND_KEYS_OPTIMIZED: \[Fp; NUM_PARTIAL_ROUNDS\] = \[(.*?)\n\];", src, re.S)
+    out["PARTIAL_ROUND_KEYS_OPTIMIZED"] = [hex(int(v)) for v in re.findall(r'Fp!\(\s*"(-?\d+)"\s*\)', m.group(1))]
+    for name in ("FULL_ROUND_KEYS_1ST_HALF", "FULL_ROUND_KEYS_2ND_HALF"):
+        m = re.search(r"pub const " + name + r": \[\[Fp; 3\]; NUM_FULL_ROUNDS / 2\] = \[(.*?)\n\];", src, re.S)
+        v = [int(x) for x in re.findall(r'Fp!\(\s*"(-?\d+)"\s*\)', m.group(1))]
+        out[name] = [[hex(x) for x in v[3 * i:3 * i + 3]] for i in range(4)]
+    m = re.search(r"pub const PARTIAL_ROUND_KEYS: \[\[Fp; 3\]; NUM_PARTIAL_ROUNDS\] = \[(.*?)\n\];", src, re.S)
+    v = [int(x) for x in re.findall(r'Fp!\(\s*"(-?\d+)"\s*\)', m.group(1))]
+    out["PARTIAL_ROUND_KEYS"] = [[hex(x) for x in v[3 * i:3 * i + 3]] for i in range(83)]
+    with open(os.path.join(HERE, "poseidon_params.json"), "w") as f:
+        json.dump(out, f, separators=(",", ":"))
+
+
+if __name__ == "__main__":
+    poseidon_params()
