@@ -538,3 +538,469 @@ def load_example(directory):
     regs = read_register_states(os.path.join(directory, "trace.bin"))
     mem = read_memory(os.path.join(directory, "memory.bin"))
     return RecursiveTrace(pub, regs, mem)
+
+
+# =====================================================================================================================
+# starknet layout (layouts/src/starknet/{mod,trace,air}.rs): the same CPU / memory / range-check / Pedersen / bitwise logic on
+# the starknet cell map, plus the ECDSA, EC-op and Poseidon builtins.
+EC_ORDER = 3618502788666131213697322783095070105526743751716087489154079457884512865583          # builtins/src/utils.rs:134
+EC_GEN = (874739451078007766457464989774322083649278607533249481151382481072868806602, 152666792071518830868575557812948353041420400780739481342941381225525861407)
+EC_BETA = 3141592653589793238462643383279502884197169399375105820974944592307816406665
+SHIFT_POINT = PEDERSEN_POINTS[0]                                                                  # ecdsa/mod.rs SHIFT_POINT = P0
+
+SN = dict(CYCLE=16, PUB_MEM_STEP=8, PEDERSEN_RATIO=32, RC_RATIO=16, ECDSA_RATIO=2048, BITWISE_RATIO=64, EC_OP_RATIO=1024, POSEIDON_RATIO=32,
+          DILUTED_STEP=8)                                                                         # starknet/mod.rs:14-49
+SN_NPC = dict(Pc=0, Instruction=1, PubMemAddr=2, PubMemVal=3, MemOp0Addr=4, MemOp0=5, PedersenInput0Addr=6, PedersenInput1Addr=262,
+              PedersenOutputAddr=134, RangeCheck128Addr=70, EcdsaPubkeyAddr=390, EcdsaMessageAddr=16774, BitwisePoolAddr=198, BitwiseXOrYAddr=902,
+              EcOpPXAddr=8582, EcOpPYAddr=4486, EcOpQXAddr=12678, EcOpQYAddr=2438, EcOpMAddr=10630, EcOpRXAddr=6534, EcOpRYAddr=14726,
+              PoseidonInput0Addr=38, PoseidonInput1Addr=102, PoseidonInput2Addr=166, PoseidonOutput0Addr=230, PoseidonOutput1Addr=294,
+              PoseidonOutput2Addr=358, MemDstAddr=8, MemDst=9, MemOp1Addr=12, MemOp1=13, UnusedAddr=14, UnusedVal=15)     # air.rs:2914-3101
+SN_AUX = dict(Ap=0, Tmp0=2, Op0MulOp1=4, Fp=8, Tmp1=10, Res=12)
+SN_ECDSA = dict(PubkeyDoublingX=1, PubkeyDoublingY=33, PubkeyDoublingSlope=35, PubkeyPartialSumX=17, PubkeyPartialSumY=49, PubkeyPartialSumXDiffInv=51,
+                PubkeyPartialSumSlope=19, RSuffix=9, MessageSuffix=59, GeneratorPartialSumY=91, GeneratorPartialSumX=27, GeneratorPartialSumXDiffInv=7,
+                GeneratorPartialSumSlope=123, RPointSlope=16331, RPointXDiffInv=32715, RInv=16355, WInv=32739, MessageInv=16363, PubkeyXSquared=32747,
+                BSlope=32763, BXDiffInv=32647)                                                    # air.rs:2691-2782
+SN_ECOP = dict(QDoublingX=41, QDoublingY=25, QDoublingSlope=57, RPartialSumX=5, RPartialSumY=37, RPartialSumSlope=11, RPartialSumXDiffInv=43, MSuffix=21,
+               MBit251AndBit196AndBit192=16371, MBit251AndBit196=16339)
+SN_POSEIDON = dict(Full0=53, Full0Sq=29, Full1=13, Full1Sq=61, Full2=45, Full2Sq=3, Partial0=3, Partial0Sq=7, Partial1=6, Partial1Sq=14)   # air.rs:2593-2602
+SN_BITWISE_SHIFTED = (9, 521, 265, 777)
+
+
+def ec_neg(p):
+    return p[0], -p[1] % P
+
+
+def ec_mul(k, pt):
+    acc = None
+    while k:
+        if k & 1:
+            acc = pt if acc is None else ec_add(acc, pt)
+        pt = ec_add(pt, pt)
+        k >>= 1
+    return acc
+
+
+def doubling_steps(num, pt):
+    """ecdsa/mod.rs doubling_steps: (point, tangent slope) for num successive doublings."""
+    out = []
+    for _ in range(num):
+        out.append((pt, ec_slope(pt, pt)))
+        pt = ec_add(pt, pt)
+    return out
+
+
+def ec_mad_steps(x, point, shift, max_doublings):
+    """gen_ec_mad_steps (ecdsa/mod.rs:166-211; ec_op/mod.rs:102-135 with max_doublings = 256): 256 steps of
+    (partial sum, fixed point, suffix, slope, 1 / (partial.x - point.x)) for shift + x * point."""
+    partial, out = shift, []
+    for i in range(256):
+        suffix = x >> i
+        slope, nxt = 0, partial
+        if suffix & 1:
+            slope = ec_slope(point, partial)
+            nxt = ec_add(partial, point)
+        out.append((partial, point, suffix, slope, pow((partial[0] - point[0]) % P, -1, P)))
+        partial = nxt
+        if i < max_doublings:
+            point = ec_add(point, point)
+    return out
+
+
+def mimic_ec_mad(m, point, shift):
+    """mimic_ec_mad_air: shift + m * point the way the AIR computes it."""
+    partial = shift
+    while m:
+        assert partial[0] != point[0]
+        if m & 1:
+            partial = ec_add(partial, point)
+        point = ec_add(point, point)
+        m >>= 1
+    return partial
+
+
+_ecdsa_dummy = None
+
+
+def ecdsa_dummy_trace():
+    """ecdsa::InstanceTrace::new(gen_dummy_instance(0)) (ecdsa/mod.rs:67-140, 229-275): private key 1, message pedersen(1, 0)."""
+    global _ecdsa_dummy
+    if _ecdsa_dummy is not None:
+        return _ecdsa_dummy
+    message = pedersen_hash(1, 0)
+    assert 0 < message < 2**251
+    k = 1
+    while True:
+        r = ec_mul(k, EC_GEN)[0]
+        if 0 < r < 2**251 and (message + r) % EC_ORDER:
+            w = k * pow((message + r) % EC_ORDER, -1, EC_ORDER) % EC_ORDER
+            if 0 < w < 2**251:
+                break
+        k += 1
+    pubkey, shift = EC_GEN, SHIFT_POINT
+    zg = mimic_ec_mad(message, EC_GEN, ec_neg(shift))
+    qr = mimic_ec_mad(r, pubkey, shift)
+    b = ec_add(zg, qr)
+    wb = mimic_ec_mad(w, b, shift)
+    assert ec_add(wb, ec_neg(shift))[0] == r                          # the signature verifies
+    t = dict(message=message, pubkey=pubkey, r=r, w=w,
+             zg_steps=ec_mad_steps(message, EC_GEN, ec_neg(shift), 250), rq_steps=ec_mad_steps(r, pubkey, shift, 255), wb_steps=ec_mad_steps(w, b, shift, 255),
+             pubkey_doubling=doubling_steps(256, pubkey), b_doubling=doubling_steps(256, b),
+             b_slope=ec_slope(zg, qr), b_x_diff_inv=pow((zg[0] - qr[0]) % P, -1, P), w_inv=pow(w, -1, P), r_inv=pow(r, -1, P),
+             message_inv=pow(message, -1, P), r_point_slope=ec_slope(wb, ec_neg(shift)), r_point_x_diff_inv=pow((wb[0] - shift[0]) % P, -1, P))
+    assert t["zg_steps"][-1][0] == zg and t["rq_steps"][-1][0] == qr and t["wb_steps"][-1][0] == wb
+    _ecdsa_dummy = t
+    return t
+
+
+_ec_op_dummy = None
+
+
+def ec_op_dummy_trace():
+    """ec_op::InstanceTrace::new(gen_dummy_instance(0)) (ec_op/mod.rs:35-100): r = P0 + 1 * G."""
+    global _ec_op_dummy
+    if _ec_op_dummy is None:
+        p, q, m = PEDERSEN_POINTS[0], EC_GEN, 1
+        steps = ec_mad_steps(m, q, p, 256)
+        _ec_op_dummy = dict(p=p, q=q, m=m, r=mimic_ec_mad(m, q, p), r_steps=steps, q_doubling=doubling_steps(256, q))
+        assert steps[-1][0] == _ec_op_dummy["r"]
+    return _ec_op_dummy
+
+
+_poseidon_cache: dict = {}
+
+
+def poseidon_trace(inputs, params):
+    """poseidon::InstanceTrace::new (poseidon/mod.rs:66-128)."""
+    key = tuple(inputs)
+    if key in _poseidon_cache:
+        return _poseidon_cache[key]
+    mds = lambda s: [(3 * s[0] + s[1] + s[2]) % P, (s[0] - s[1] + s[2]) % P, (s[0] + s[1] - 2 * s[2]) % P]        # params.rs:15-19
+
+    def half(state, keys):
+        rounds = []
+        for rk in keys:
+            state = [(s + k) % P for s, k in zip(state, rk)]
+            rounds.append(list(state))
+            state = mds([pow(s, 3, P) for s in state])
+        return rounds, state
+
+    first, state = half([v % P for v in inputs], params["full1"])
+    partial = []
+    for rk in params["partial_opt"]:
+        state[2] = (state[2] + rk) % P
+        partial.append(state[2])
+        state[2] = pow(state[2], 3, P)
+        state = mds(state)
+    keys2 = [list(k) for k in params["full2"]]
+    keys2[0] = [2841653098167170594677968593255398661749780759922623066311132183067080032372,
+                3013664908435951456462052676857400233978317167153628607151632758126998548956,
+                1580909581709481477620907470438960344056357690169203419381231226301063390430]                       # poseidon/mod.rs:100-104
+    second, out = half(state, keys2)
+    # cross-check against the plain permutation (poseidon/mod.rs:166-197)
+    s, rnd = [v % P for v in inputs], 0
+    allk = params["full1"] + params["partial"] + params["full2"]
+    for _ in range(4):
+        s = mds([pow((a + k) % P, 3, P) for a, k in zip(s, allk[rnd])]); rnd += 1
+    for _ in range(83):
+        s = [(a + k) % P for a, k in zip(s, allk[rnd])]; s[2] = pow(s[2], 3, P); s = mds(s); rnd += 1
+    for _ in range(4):
+        s = mds([pow((a + k) % P, 3, P) for a, k in zip(s, allk[rnd])]); rnd += 1
+    assert s == out, "optimised Poseidon schedule differs from the plain permutation"
+    _poseidon_cache[key] = dict(full=first + second, partial=partial, out=out)
+    return _poseidon_cache[key]
+
+
+def load_poseidon_params(path):
+    d = json.load(open(path))
+    h = lambda v: int(v, 16)
+    return dict(full1=[[h(x) for x in r] for r in d["FULL_ROUND_KEYS_1ST_HALF"]], full2=[[h(x) for x in r] for r in d["FULL_ROUND_KEYS_2ND_HALF"]],
+                partial=[[h(x) for x in r] for r in d["PARTIAL_ROUND_KEYS"]], partial_opt=[h(x) for x in d["PARTIAL_ROUND_KEYS_OPTIMIZED"]])
+
+
+class StarknetTrace:
+    """ExecutionTrace::new of the starknet layout (layouts/src/starknet/trace.rs:98-995).  private_input: "pedersen" [(index, a, b)],
+    "range_check" [(index, value)], "bitwise" [(index, x, y)]; the ECDSA / EC-op / Poseidon builtins are filled with the reference's
+    dummy instances (the committed bootloader fixture has none of its own)."""
+
+    def __init__(self, public_input: AirPublicInput, register_states, memory, poseidon_params, private_input=None):
+        priv = private_input or {}
+        priv = {k: priv.get(k, []) for k in ("pedersen", "range_check", "bitwise")}
+        self.public_input = public_input
+        num_cycles = len(register_states)
+        assert num_cycles & (num_cycles - 1) == 0
+        n = self.trace_len = num_cycles * 16
+        self.public_memory = list(public_input.public_memory)
+        padding = self.padding_entry = public_input.public_memory_padding()
+        seg = public_input.memory_segments
+        words = {}
+
+        def word_at(pc):
+            if pc not in words:
+                words[pc] = Word(memory[pc])
+            return words[pc]
+
+        flags = [0] * n
+        npc = [padding[0], padding[1]] * (n // 2)
+        rc_pool = []
+        for ap, fp, pc in register_states:
+            w = word_at(pc)
+            rc_pool += [w.get_off_dst(), w.get_off_op0(), w.get_off_op1()]
+        rc128 = [(idx, val, RecursiveTrace._rc_parts(val)) for idx, val in priv["range_check"]]
+        for _, _, parts in rc128:
+            rc_pool += parts
+        ordered_rc, rc_padding = ordered_with_padding(rc_pool)
+        self.range_check_min, self.range_check_max = min(rc_pool), max(rc_pool)
+        rc_max = self.range_check_max
+        ordered_rc, rc_padding = iter(ordered_rc), iter(rc_padding)
+        rc_col = [rc_max] * n
+        aux = [0] * n
+        N, A = SN_NPC, SN_AUX
+        for c, (ap, fp, pc) in enumerate(register_states):                     # trace.rs:186-251
+            w, o = word_at(pc), c * 16
+            op0, op1, dst = w.get_op0(ap, fp, memory), w.get_op1(pc, ap, fp, memory), w.get_dst(ap, fp, memory)
+            for f in range(16):
+                flags[o + f] = w.get_flag_prefix(f)
+            npc[o + N["Pc"]], npc[o + N["Instruction"]] = pc, w.w
+            npc[o + N["MemOp0Addr"]], npc[o + N["MemOp0"]] = w.get_op0_addr(ap, fp), op0
+            npc[o + N["MemDstAddr"]], npc[o + N["MemDst"]] = w.get_dst_addr(ap, fp), dst
+            npc[o + N["MemOp1Addr"]], npc[o + N["MemOp1"]] = w.get_op1_addr(pc, ap, fp, memory), op1
+            for off in range(0, 16, SN["PUB_MEM_STEP"]):
+                npc[o + off + N["PubMemAddr"]] = npc[o + off + N["PubMemVal"]] = 0
+            rc_col[o + RANGE_CHECK["OffDst"]], rc_col[o + RANGE_CHECK["OffOp1"]], rc_col[o + RANGE_CHECK["OffOp0"]] = \
+                w.get_off_dst(), w.get_off_op1(), w.get_off_op0()
+            aux[o + A["Tmp0"]], aux[o + A["Tmp1"]] = w.get_tmp0(ap, fp, memory), w.get_tmp1(pc, ap, fp, memory)
+            aux[o + A["Ap"]], aux[o + A["Fp"]] = ap, fp
+            aux[o + A["Op0MulOp1"]], aux[o + A["Res"]] = op0 * op1 % P, w.get_res(pc, ap, fp, memory)
+        for index in range(len(rc128), num_cycles // SN["RC_RATIO"]):          # :253-270
+            value = 0
+            for _ in range(8):
+                value = (value << 16) + next(rc_padding, rc_max)
+            rc128.append((index, value, RecursiveTrace._rc_parts(value)))
+        for cycle in range(num_cycles):                                        # :272-298
+            o = cycle * 16
+            if cycle % 2 == 1:
+                rc_col[o + RANGE_CHECK["Unused"]] = next(rc_padding, rc_max)
+            for off in range(0, 16, RANGE_CHECK_STEP):
+                rc_col[o + off + RANGE_CHECK["Ordered"]] = next(ordered_rc, rc_max)
+        assert next(rc_padding, None) is None and next(ordered_rc, None) is None
+        for o in range(0, n, SN["DILUTED_STEP"]):                              # diluted cells share the column: clear them (:304-313)
+            rc_col[o + 1] = rc_col[o + 5] = 0
+        # Pedersen: one step per row, 512 rows per hash, its own four columns (:315-387)
+        ped_x, ped_y, ped_suffix, ped_slope = [0] * n, [0] * n, [0] * n, [0] * n
+        ped_begin = seg["pedersen"][0]
+        instances = list(priv["pedersen"])
+        for k in range(n // 512):
+            index, a, b = instances[k] if k < len(instances) else (k, 0, 0)
+            t, base = pedersen_instance_trace(a % P, b % P), k * 512
+            for s, (pt, suffix, slope) in enumerate(t["steps"]):
+                ped_x[base + s], ped_y[base + s] = pt
+                ped_suffix[base + s], ped_slope[base + s] = suffix % P, slope
+            (a3, a2), (b3, b2) = t["a_flags"], t["b_flags"]
+            ped_slope[base + 255], ped_slope[base + 256 + 255] = a2, b2          # Pedersen::Bit251AndBit196 = 255 (column 4)
+            aux[base + 71], aux[base + 256 + 71] = a3, b3                          # Bit251AndBit196AndBit192 = 71 (column 8)
+            addr = ped_begin + index * 3
+            npc[base + N["PedersenInput0Addr"]], npc[base + N["PedersenInput0Addr"] + 1] = addr, a % P
+            npc[base + N["PedersenInput1Addr"]], npc[base + N["PedersenInput1Addr"] + 1] = addr + 1, b % P
+            npc[base + N["PedersenOutputAddr"]], npc[base + N["PedersenOutputAddr"] + 1] = addr + 2, t["output"]
+        # range-check builtin: 256 rows per value (:389-425)
+        rc_begin = seg["range_check"][0]
+        for k in range(n // 256):
+            index, value, parts = rc128[k]
+            base = k * 256
+            for j, part in enumerate(parts):
+                rc_col[base + RC_BUILTIN_COMPONENT + 32 * j] = part
+            npc[base + N["RangeCheck128Addr"]], npc[base + N["RangeCheck128Addr"] + 1] = rc_begin + index, value % P
+        # ECDSA: 32768 rows per signature, all dummies (:427-525)
+        E = SN_ECDSA
+        ec_begin = seg["ecdsa"][0]
+        t = ecdsa_dummy_trace()
+        for k in range(n // 32768):
+            base = k * 32768
+            for half, (steps, dbl) in enumerate(((t["rq_steps"], t["pubkey_doubling"]), (t["wb_steps"], t["b_doubling"]))):
+                for i in range(256):
+                    r = base + 64 * (256 * half + i)
+                    (partial, _, suffix, slope, xdi), (dpt, dslope) = steps[i], dbl[i]
+                    aux[r + E["PubkeyDoublingX"]], aux[r + E["PubkeyDoublingY"]], aux[r + E["PubkeyDoublingSlope"]] = dpt[0], dpt[1], dslope
+                    aux[r + E["PubkeyPartialSumX"]], aux[r + E["PubkeyPartialSumY"]] = partial
+                    aux[r + E["PubkeyPartialSumSlope"]], aux[r + E["PubkeyPartialSumXDiffInv"]], aux[r + E["RSuffix"]] = slope, xdi, suffix % P
+            for i in range(256):
+                r = base + 128 * i
+                partial, _, suffix, slope, xdi = t["zg_steps"][i]
+                aux[r + E["GeneratorPartialSumX"]], aux[r + E["GeneratorPartialSumY"]] = partial
+                aux[r + E["GeneratorPartialSumSlope"]], aux[r + E["GeneratorPartialSumXDiffInv"]], aux[r + E["MessageSuffix"]] = slope, xdi, suffix % P
+            for name, key in (("BSlope", "b_slope"), ("BXDiffInv", "b_x_diff_inv"), ("WInv", "w_inv"), ("RInv", "r_inv"), ("RPointSlope", "r_point_slope"),
+                              ("RPointXDiffInv", "r_point_x_diff_inv"), ("MessageInv", "message_inv")):
+                aux[base + E[name]] = t[key]
+            aux[base + E["PubkeyXSquared"]] = t["pubkey"][0] ** 2 % P
+            npc[base + N["EcdsaPubkeyAddr"]], npc[base + N["EcdsaPubkeyAddr"] + 1] = ec_begin + 2 * k, t["pubkey"][0]
+            npc[base + N["EcdsaMessageAddr"]], npc[base + N["EcdsaMessageAddr"] + 1] = ec_begin + 2 * k + 1, t["message"]
+        # bitwise: 1024 rows per instance; its diluted chunks live in the range-check column (:527-649)
+        bw_begin = seg["bitwise"][0]
+        bw_instances, diluted_pool, dummy = list(priv["bitwise"]), [], None
+        for k in range(n // 1024):
+            index, x, y = bw_instances[k] if k < len(bw_instances) else (k, 0, 0)
+            base = k * 1024
+            if (x, y) == (0, 0) and dummy is not None:
+                diluted_pool += dummy
+            else:
+                before = len(diluted_pool)
+                parts = [partition256(v) for v in (x, y, x & y, x ^ y)]
+                v = [parts[2][3][j] + parts[3][3][j] for j in range(4)]
+                for j, sh in enumerate((4, 4, 4, 8)):
+                    s = v[j] << sh
+                    diluted_pool.append(undilute(s))
+                    rc_col[base + SN_BITWISE_SHIFTED[j]] = s
+                for q, part in enumerate(parts):
+                    for chunk in range(4):
+                        for j in range(4):
+                            rc_col[base + 256 * q + 1 + 16 * (4 * chunk + j)] = part[chunk][j]
+                            diluted_pool.append(undilute(part[chunk][j]))
+                if (x, y) == (0, 0):
+                    dummy = diluted_pool[before:]
+            o = base + N["BitwisePoolAddr"]
+            for j, val in enumerate((x, y, x & y, x ^ y)):
+                npc[o + 256 * j], npc[o + 256 * j + 1] = bw_begin + index * 5 + j, val % P
+            npc[base + N["BitwiseXOrYAddr"]], npc[base + N["BitwiseXOrYAddr"] + 1] = bw_begin + index * 5 + 4, (x | y) % P
+        ordered_dil, dil_padding = ordered_with_padding(diluted_pool, 0, (1 << DILUTED_CHECK_N_BITS) - 1)
+        ordered_dil, dil_padding = [dilute(v) for v in ordered_dil], iter(dilute(v) for v in dil_padding)
+        done = False                                                            # padding into the odd diluted steps (:666-693)
+        for base in range(0, n, 1024):
+            for i in range(1, 128, 2):
+                off = i * 8 + 1
+                if off in SN_BITWISE_SHIFTED:
+                    continue
+                v = next(dil_padding, None)
+                if v is None:
+                    done = True
+                    break
+                rc_col[base + off] = v
+            if done:
+                break
+        steps = n // 8
+        for k, v in enumerate(ordered_dil):                                     # :695-701
+            rc_col[8 * (steps - len(ordered_dil) + k) + 5] = v
+        assert next(dil_padding, None) is None
+        # EC-op: 16384 rows per instance, all dummies (:708-777)
+        O = SN_ECOP
+        eo_begin = seg["ec_op"][0]
+        t = ec_op_dummy_trace()
+        for k in range(n // 16384):
+            base = k * 16384
+            for i in range(256):
+                r = base + 64 * i
+                (dpt, dslope), (partial, _, suffix, slope, xdi) = t["q_doubling"][i], t["r_steps"][i]
+                aux[r + O["QDoublingX"]], aux[r + O["QDoublingY"]], aux[r + O["QDoublingSlope"]] = dpt[0], dpt[1], dslope
+                aux[r + O["RPartialSumX"]], aux[r + O["RPartialSumY"]], aux[r + O["MSuffix"]] = partial[0], partial[1], suffix % P
+                if i != 255:
+                    aux[r + O["RPartialSumSlope"]], aux[r + O["RPartialSumXDiffInv"]] = slope, xdi
+            aux[base + O["MBit251AndBit196"]] = aux[base + O["MBit251AndBit196AndBit192"]] = 0
+            for j, (name, val) in enumerate((("EcOpPXAddr", t["p"][0]), ("EcOpPYAddr", t["p"][1]), ("EcOpQXAddr", t["q"][0]), ("EcOpQYAddr", t["q"][1]),
+                                             ("EcOpMAddr", t["m"]), ("EcOpRXAddr", t["r"][0]), ("EcOpRYAddr", t["r"][1]))):
+                npc[base + N[name]], npc[base + N[name] + 1] = eo_begin + 7 * k + j, val
+        # Poseidon: 512 rows per instance, all-zero inputs (:779-873)
+        Q = SN_POSEIDON
+        po_begin = seg["poseidon"][0]
+        t = poseidon_trace((0, 0, 0), poseidon_params)
+        for k in range(n // 512):
+            base = k * 512
+            for i, st in enumerate(t["full"]):
+                r = base + 64 * i
+                for j, (cell, sq) in enumerate((("Full0", "Full0Sq"), ("Full1", "Full1Sq"), ("Full2", "Full2Sq"))):
+                    aux[r + Q[cell]], aux[r + Q[sq]] = st[j], st[j] * st[j] % P
+            for i, v in enumerate(t["partial"][:64]):
+                rc_col[base + 8 * i + Q["Partial0"]], rc_col[base + 8 * i + Q["Partial0Sq"]] = v, v * v % P
+            for i, v in enumerate(t["partial"][61:]):
+                aux[base + 16 * i + Q["Partial1"]], aux[base + 16 * i + Q["Partial1Sq"]] = v, v * v % P
+            for j, (name, val) in enumerate((("PoseidonInput0Addr", 0), ("PoseidonInput1Addr", 0), ("PoseidonInput2Addr", 0),
+                                             ("PoseidonOutput0Addr", t["out"][0]), ("PoseidonOutput1Addr", t["out"][1]), ("PoseidonOutput2Addr", t["out"][2]))):
+                npc[base + N[name]], npc[base + N[name] + 1] = po_begin + 6 * k + j, val
+        # memory (:875-929)
+        accesses = [(npc[i], npc[i + 1]) for i in range(0, n, 2)]
+        srt = sorted(accesses + self.public_memory, key=lambda e: e[0])
+        gaps = []
+        for (a, _), (b, _) in zip(srt, srt[1:]):
+            gaps.extend(range(a + 1, b))
+        gaps = iter(gaps)
+        for o in range(0, n, 16):
+            addr = next(gaps, None)
+            if addr is None:
+                break
+            npc[o + N["UnusedAddr"]], npc[o + N["UnusedVal"]] = addr, 0
+        assert next(gaps, None) is None
+        accesses = [(npc[i], npc[i + 1]) for i in range(0, n, 2)]
+        cells = n // SN["PUB_MEM_STEP"]
+        ordered = sorted(accesses + [padding] * (cells - len(self.public_memory)) + self.public_memory, key=lambda e: e[0])
+        zeros, ordered = ordered[:cells], ordered[cells:]
+        assert all(a == 0 for a, _ in zeros) and ordered[0][0] == 1
+        for cur, nxt in zip(ordered, ordered[1:]):
+            assert cur == nxt or cur[0] == nxt[0] - 1, (cur, nxt)
+        memory_col = [v for e in ordered for v in e]
+        assert len(memory_col) == n
+        self.base_columns = [flags, ped_x, ped_y, ped_suffix, ped_slope, npc, memory_col, rc_col, aux]        # trace.rs:931-941
+        self.initial_registers, self.final_registers = register_states[0], register_states[-1]
+
+    def build_extension_columns(self, challenges):
+        """starknet/trace.rs:997-1100: ONE extension column."""
+        n = self.trace_len
+        npc, mem, rc = self.base_columns[5], self.base_columns[6], self.base_columns[7]
+
+        def running_quotient(num_factors, den_factors):
+            nums, dens, a, b = [], [], 1, 1
+            for f, g in zip(num_factors, den_factors):
+                a, b = a * f % P, b * g % P
+                nums.append(a)
+                dens.append(b)
+            return [x * y % P for x, y in zip(nums, batch_inverse(dens))], a, b
+
+        perm = [0] * n
+        z, alpha = challenges[MEM_Z], challenges[MEM_A]
+        perm[0::2], _, _ = running_quotient(((z - (alpha * npc[i + 1] + npc[i])) % P for i in range(0, n, 2)),
+                                            ((z - (alpha * mem[i + 1] + mem[i])) % P for i in range(0, n, 2)))
+        z = challenges[RC_Z]
+        perm[1::4], a, b = running_quotient(((z - rc[i]) % P for i in range(0, n, 4)), ((z - rc[i + 2]) % P for i in range(0, n, 4)))
+        assert a == b
+        z = challenges[DILUTED_PERM_Z]
+        perm[7::8], a, b = running_quotient(((z - rc[i + 1]) % P for i in range(0, n, 8)), ((z - rc[i + 5]) % P for i in range(0, n, 8)))
+        assert a == b
+        z, alpha = challenges[DILUTED_AGG_Z], challenges[DILUTED_AGG_A]
+        acc = 1
+        perm[3] = 1
+        for i in range(1, n // 8):
+            u = (rc[8 * i + 5] - rc[8 * (i - 1) + 5]) % P
+            acc = (acc * (1 + z * u) + alpha * u * u) % P
+            perm[8 * i + 3] = acc
+        return [perm]
+
+    def gen_hints(self, challenges):
+        """starknet AirConfig::gen_hints (starknet/air.rs:2408-2476), PublicInputHint order (:3244-3262)."""
+        pi = self.public_input
+        s, k = self.trace_len // SN["PUB_MEM_STEP"], len(self.public_memory)
+        z, alpha = challenges[MEM_Z], challenges[MEM_A]
+        den = 1
+        for a, v in self.public_memory:
+            den = den * (z - (alpha * v + a)) % P
+        pad = pow((z - (alpha * self.padding_entry[1] + self.padding_entry[0])) % P, s - k, P)
+        quotient = pow(z, s, P) * pow(den * pad % P, -1, P) % P
+        cumulative = compute_diluted_cumulative_value(challenges[DILUTED_AGG_Z], challenges[DILUTED_AGG_A])
+        seg = pi.memory_segments
+        return [pi.initial_ap(), pi.initial_pc(), pi.final_ap(), pi.final_pc(), quotient, 1, pi.rc_min, pi.rc_max, 1, 0, cumulative,
+                seg["pedersen"][0], seg["range_check"][0], seg["ecdsa"][0], seg["bitwise"][0], seg["ec_op"][0], seg["poseidon"][0]]
+
+
+def load_bootloader(directory, poseidon_params_path):
+    """The reference's example/bootloader fixture (starknet layout, 131072 steps; trace.bin is kept gzipped in tests/golden)."""
+    import gzip
+    import os
+    import tempfile
+
+    pub = AirPublicInput.from_file(os.path.join(directory, "air-public-input.json"))
+    with tempfile.NamedTemporaryFile() as f:
+        f.write(gzip.open(os.path.join(directory, "trace.bin.gz")).read())
+        f.flush()
+        regs = read_register_states(f.name)
+    mem = read_memory(os.path.join(directory, "memory.bin"))
+    priv = json.load(open(os.path.join(directory, "air-private-input.json")))
+    private = {"pedersen": [(e["index"], int(e["x"], 16), int(e["y"], 16)) for e in priv.get("pedersen", [])],
+               "range_check": [(e["index"], int(e["value"], 16)) for e in priv.get("range_check", [])],
+               "bitwise": [(e["index"], int(e["x"], 16), int(e["y"], 16)) for e in priv.get("bitwise", [])]}
+    return StarknetTrace(pub, regs, mem, load_poseidon_params(poseidon_params_path), private)

@@ -130,3 +130,70 @@ def test_proof_of_the_example_verifies(example, oracle, claim):
     bad.fri_layers[1].flattened_rows[2] = (bad.fri_layers[1].flattened_rows[2] + 1) % P
     with pytest.raises(VerificationError):
         verify_proof(bad, hp.layout, Coin.from_public_input(tr.public_input), tr.gen_hints, kind)
+
+
+# ---- starknet layout: the reference's example/bootloader trace (n = 2^21) ---------------------------------------------------------
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def bootloader():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from oracle import cairo
+
+    tr = cairo.load_bootloader(os.path.join(GOLDEN, "bootloader"), os.path.join(GOLDEN, "poseidon_params.json"))
+    return tr, to_mont_cols(tr.base_columns)
+
+
+def test_starknet_device_extension_column_matches_the_reference_builder(bootloader, oracle):
+    import random
+
+    import sandstorm_b200 as ss
+    from sandstorm_b200.ext_columns import build_extension_columns
+
+    tr, base_np = bootloader
+    rnd = random.Random(12)
+    challenges = [rnd.randrange(P) for _ in range(6)]
+    got = build_extension_columns("starknet", ss.Matrix.from_numpy(base_np), challenges).numpy()
+    assert np.array_equal(got, to_mont_cols(tr.build_extension_columns(challenges)))
+
+
+def test_bootloader_trace_through_the_hot_path_and_the_proof_verifies(bootloader, oracle):
+    """The SHARP claim of cli/src/main.rs:90-92 (starknet layout, Solidity coin, Keccak trees) at the CLI's blowup 4: degree of the
+    composition polynomial, the verifier's OOD identity on the 195-constraint AIR, then proof -> wire -> restated verifier."""
+    import torch
+
+    import sandstorm_b200 as ss
+    from air_ref import eval_at_point
+    from sandstorm_b200.ext_columns import build_extension_columns
+    from sandstorm_b200.proof import Proof, assemble_proof
+    from sandstorm_b200.prover import HotPathProver, ProofOptions
+    from sandstorm_b200.public_coin import SolidityVerifierPublicCoin as Coin
+    from sandstorm_b200.verify import VerificationError, verify_proof
+
+    tr, base_np = bootloader
+    log_n, n = 21, tr.trace_len
+    opt = ProofOptions(num_queries=10, log_blowup=2, tree_kind=ss.TREE_KECCAK, grinding_factor=8, max_remainder_coeffs=16)
+    hp = HotPathProver("starknet", log_n, opt, coin=Coin.from_public_input(tr.public_input))
+    base = ss.Matrix.from_numpy(base_np)
+    res = hp.prove(base, lambda ch: build_extension_columns("starknet", base, ch), hints=tr.gen_hints, self_check=True, keep_openings=True)
+    torch.cuda.synchronize()
+    assert res.composition_top_zero is True, "composition polynomial is not of degree < 2n: the trace violates the transpiled AIR"
+    assert res.deep_matches_full_evaluation is True and hp.remainder_high_zero is True
+    L = hp.layout
+    tap_values = dict(zip(L.taps(), res.ood_trace))
+    z = res.ood_point
+    lhs = eval_at_point(L.composition(n), z, tap_values, log_n, res.challenges, res.hints, res.composition_coeffs)
+    assert lhs == sum(pow(z, j, P) * v for j, v in enumerate(res.ood_composition)) % P
+    proof = assemble_proof(res, opt, n)
+    wire = proof.serialize()
+    again = Proof.deserialize(wire)
+    assert again.serialize() == wire
+    verify_proof(again, L, Coin.from_public_input(tr.public_input), tr.gen_hints, ss.TREE_KECCAK)
+    bad = Proof.deserialize(wire)
+    bad.ood_trace[100] = (bad.ood_trace[100] + 1) % P
+    with pytest.raises(VerificationError):
+        verify_proof(bad, L, Coin.from_public_input(tr.public_input), tr.gen_hints, ss.TREE_KECCAK)
