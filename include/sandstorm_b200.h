@@ -134,6 +134,12 @@ ss_status ss_merkle_open(ss_ctx *ctx, const ss_tree *tree, const uint64_t *h_ind
  * levels are Pedersen (log_count <= N_FRIENDLY) and each sub-tree is built with n_friendly - log_count.
  * Synchronises. */
 ss_status ss_merkle_combine(ss_ctx *ctx, ss_tree_kind kind, const uint8_t *h_subroots, int log_count, uint8_t root[32]);
+/* The upper log_count siblings of the authentication path of any leaf under sub-tree `index`, bottom first, in
+ * ss_merkle_open's storage form: ss_merkle_open(sub-tree, local leaf) followed by these is the path through the whole
+ * tree (MerkleTree::prove, crypto/src/merkle/mod.rs:120-148).  subroots_algebraic: the sub-roots are Pedersen felts
+ * (SS_TREE_FRIENDLY with log_count < n_friendly, or a single-column tree).  Synchronises. */
+ss_status ss_merkle_combine_open(ss_ctx *ctx, ss_tree_kind kind, const uint8_t *h_subroots, int log_count, int subroots_algebraic,
+                                 uint64_t index, uint8_t *h_path /* log_count * 32 */);
 int ss_tree_log_rows(const ss_tree *tree);
 void ss_tree_free(ss_tree *tree);
 /* batch Pedersen hash (builtins/src/pedersen/mod.rs:31-36), Montgomery limbs in and out */
@@ -215,8 +221,13 @@ ss_status ss_shard_dft(ss_ctx *ctx, ss_field field, const void *d_in, uint64_t i
  *   ss_dist_init        joins the communicator (collective); world = 2, 4 or 8
  *   ss_dist_lde         one column: evaluations on <w_n> (src_on_coset: on 3<w_n>) -> evaluations on 3<w_N>, both block-cyclic
  *   ss_dist_halo        the `halo` rows that follow every owned piece of every column, from the next rank (halo <= s)
- *   ss_dist_commit      MatrixMerkleTree::from_matrix over all ranks' rows in bit-reversed leaf order -> root (collective, synchronises)
- *   ss_dist_allgather   in-place all-gather of a block-cyclic vector */
+ *   ss_dist_commit      MatrixMerkleTree::from_matrix over all ranks' rows in bit-reversed leaf order -> root (collective, synchronises);
+ *                       out_subtree (nullable): this rank's sub-tree over leaves [rank N/W, (rank+1) N/W), kept for ss_dist_open and
+ *                       freed by the caller; out_subroots (nullable, 32 W bytes): every rank's sub-root
+ *   ss_dist_allgather   in-place all-gather of a block-cyclic vector
+ *   ss_dist_open        MerkleTree::prove for n leaf positions of the whole tree (collective: the owner of a leaf range opens its
+ *                       sub-tree, the upper siblings come from the sub-roots; every rank receives every path, n * log_rows * 32 bytes)
+ *   ss_dist_gather_rows Matrix::read_row for n natural row indices of a block-cyclic matrix (collective; every rank receives every row) */
 ss_status ss_dist_unique_id(ss_ctx *ctx, uint8_t id[128]);
 ss_status ss_dist_init(ss_ctx *ctx, const uint8_t id[128], int rank, int world);
 ss_status ss_dist_finalize(ss_ctx *ctx);
@@ -225,7 +236,11 @@ ss_status ss_dist_lde(ss_ctx *ctx, ss_field field, const void *d_src, int log_n,
 ss_status ss_dist_halo(ss_ctx *ctx, void *d_cols, uint64_t col_stride, int n_cols, int log_rows, uint64_t halo, void *stream);
 ss_status ss_dist_allgather(ss_ctx *ctx, void *d_vec, int log_rows, void *stream);
 ss_status ss_dist_commit(ss_ctx *ctx, ss_tree_kind kind, int n_friendly, const void *d_cols, uint64_t col_stride, int n_cols,
-                         int log_rows, uint8_t root[32], void *stream);
+                         int log_rows, uint8_t root[32], ss_tree **out_subtree, uint8_t *out_subroots, void *stream);
+ss_status ss_dist_open(ss_ctx *ctx, ss_tree_kind kind, int subroots_algebraic, const ss_tree *subtree, const uint8_t *h_subroots,
+                       const uint64_t *h_positions, size_t n, uint8_t *h_paths, void *stream);
+ss_status ss_dist_gather_rows(ss_ctx *ctx, const void *d_cols, uint64_t col_stride, int n_cols, int log_rows, const uint64_t *h_indices,
+                              size_t n, void *h_rows, void *stream);
 
 /* ------------------------------------------------------------------ extension columns (§8 f1)
  * Trace::build_extension_columns (layouts/src/recursive/trace.rs:699-814, starknet/trace.rs:997-1100) as device prefix

@@ -44,6 +44,7 @@ SIGNATURES = {
     "ss_merkle_leaves": (c_int, [c_void_p, c_void_p, POINTER(c_uint64), c_size_t, POINTER(c_uint8)]),
     "ss_merkle_open": (c_int, [c_void_p, c_void_p, POINTER(c_uint64), c_size_t, POINTER(c_uint8)]),
     "ss_merkle_combine": (c_int, [c_void_p, c_int, POINTER(c_uint8), c_int, POINTER(c_uint8)]),
+    "ss_merkle_combine_open": (c_int, [c_void_p, c_int, POINTER(c_uint8), c_int, c_int, c_uint64, POINTER(c_uint8)]),
     "ss_tree_log_rows": (c_int, [c_void_p]),
     "ss_tree_free": (None, [c_void_p]),
     "ss_pedersen_hash": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -61,7 +62,9 @@ SIGNATURES = {
     "ss_dist_lde": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "ss_dist_halo": (c_int, [c_void_p, c_void_p, c_uint64, c_int, c_int, c_uint64, c_void_p]),
     "ss_dist_allgather": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
-    "ss_dist_commit": (c_int, [c_void_p, c_int, c_int, c_void_p, c_uint64, c_int, c_int, POINTER(c_uint8), c_void_p]),
+    "ss_dist_commit": (c_int, [c_void_p, c_int, c_int, c_void_p, c_uint64, c_int, c_int, POINTER(c_uint8), POINTER(c_void_p), POINTER(c_uint8), c_void_p]),
+    "ss_dist_open": (c_int, [c_void_p, c_int, c_int, c_void_p, POINTER(c_uint8), POINTER(c_uint64), c_size_t, POINTER(c_uint8), c_void_p]),
+    "ss_dist_gather_rows": (c_int, [c_void_p, c_void_p, c_uint64, c_int, c_int, POINTER(c_uint64), c_size_t, c_void_p, c_void_p]),
     "ss_perm_product": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_uint64, c_uint64, c_void_p, c_void_p, c_void_p, c_uint64, c_void_p]),
     "ss_diluted_aggregate": (c_int, [c_void_p, c_int, c_void_p, c_uint64, c_uint64, c_void_p, c_void_p, c_void_p, c_uint64, c_void_p]),
     "ss_constraint_eval": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_uint64, c_int, c_int, c_int, c_uint64, c_uint64, c_int, c_void_p, c_void_p]),

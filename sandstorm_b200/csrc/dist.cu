@@ -11,6 +11,7 @@
 //   ss_dist_halo         after an LDE phase: the `halo` rows that follow every owned piece, from the next rank
 //   ss_dist_commit       bit-reversed-order Merkle root of a block-cyclic matrix (digest all-to-all + sub-trees + combine)
 //   ss_dist_allgather    in-place all-gather of a block-cyclic vector (the DEEP evaluations before FRI)
+//   ss_dist_open / ss_dist_gather_rows    query phase: authentication paths through the sharded tree, opened rows (collective)
 #include "ctx.h"
 #include <dlfcn.h>
 #include <cstring>
@@ -31,6 +32,7 @@ struct NcclApi {
     int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
@@ -50,10 +52,11 @@ NcclApi &nccl() {
     api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
     api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
     api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
+    api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
     api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
     api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
     api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
-    if (api.GetUniqueId && api.CommInitRank && api.Send && api.Recv && api.AllGather && api.GroupStart && api.GroupEnd) api.lib = h;
+    if (api.GetUniqueId && api.CommInitRank && api.Send && api.Recv && api.AllGather && api.AllReduce && api.GroupStart && api.GroupEnd) api.lib = h;
     return api;
 }
 
@@ -241,7 +244,7 @@ ss_status ss_dist_allgather(ss_ctx *ctx, void *d_vec, int log_rows, void *stream
 }
 
 ss_status ss_dist_commit(ss_ctx *ctx, ss_tree_kind kind, int n_friendly, const void *d_cols, uint64_t col_stride, int n_cols,
-                         int log_rows, uint8_t root[32], void *stream) {
+                         int log_rows, uint8_t root[32], ss_tree **out_subtree, uint8_t *out_subroots, void *stream) {
     if (!ctx) return SS_ERR_INVALID;
     Dist *d;
     ss_status rc = get(ctx, &d);
@@ -278,8 +281,9 @@ ss_status ss_dist_commit(ss_ctx *ctx, ss_tree_kind kind, int n_friendly, const v
     if (rc) return done(rc);
     uint8_t sub[32];
     rc = ss_merkle_root(ctx, tree, sub);
-    ss_tree_free(tree);
+    if (rc || !out_subtree) ss_tree_free(tree);
     if (rc) return done(rc);
+    if (out_subtree) *out_subtree = tree;                   // kept for ss_dist_open; the caller frees it
     // all-gather of the W sub-roots through a small device buffer
     uint8_t *d_roots = recv;
     SS_CUDA_CHECK(ctx, cudaMemcpyAsync(d_roots + 32 * r, sub, 32, cudaMemcpyHostToDevice, st));
@@ -287,8 +291,78 @@ ss_status ss_dist_commit(ss_ctx *ctx, ss_tree_kind kind, int n_friendly, const v
     uint8_t subs[8 * 32];
     SS_CUDA_CHECK(ctx, cudaMemcpyAsync(subs, d_roots, 32 * (size_t)W, cudaMemcpyDeviceToHost, st));
     SS_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    if (out_subroots) memcpy(out_subroots, subs, 32 * (size_t)W);
     rc = ss_merkle_combine(ctx, kind, subs, log_w, root);
     return done(rc);
+}
+
+// every rank contributes the bytes of the slots it owns (zero elsewhere): sum = the whole buffer, on every rank
+static ss_status share_bytes(ss_ctx *ctx, Dist *d, uint8_t *h_buf, size_t bytes, cudaStream_t st) {
+    uint8_t *dev = nullptr;
+    SS_CUDA_CHECK(ctx, dev_alloc(ctx, reinterpret_cast<void **>(&dev), bytes));
+    cudaMemcpyAsync(dev, h_buf, bytes, cudaMemcpyHostToDevice, st);
+    const int r = nccl().AllReduce(dev, dev, bytes, NCCL_UINT8, /*ncclSum*/ 0, d->comm, st);
+    cudaMemcpyAsync(h_buf, dev, bytes, cudaMemcpyDeviceToHost, st);
+    const cudaError_t e = cudaStreamSynchronize(st);
+    dev_free(ctx, dev);
+    if (r != 0) return fail(ctx, SS_ERR_CUDA, "ncclAllReduce failed: %s", nccl().GetErrorString ? nccl().GetErrorString(r) : "?");
+    if (e != cudaSuccess) return fail(ctx, SS_ERR_CUDA, "ss_dist: %s", cudaGetErrorString(e));
+    return SS_OK;
+}
+
+ss_status ss_dist_open(ss_ctx *ctx, ss_tree_kind kind, int subroots_algebraic, const ss_tree *subtree, const uint8_t *h_subroots,
+                       const uint64_t *h_positions, size_t n, uint8_t *h_paths, void *stream) {
+    if (!ctx) return SS_ERR_INVALID;
+    Dist *d;
+    ss_status rc = get(ctx, &d);
+    if (rc) return rc;
+    if (!subtree || !h_subroots || (n && (!h_positions || !h_paths))) return fail(ctx, SS_ERR_INVALID, "ss_dist_open: bad arguments");
+    if (n == 0) return SS_OK;
+    const int sub_log = ss_tree_log_rows(subtree), log_w = d->log_w, depth = sub_log + log_w;
+    std::vector<uint64_t> local;
+    std::vector<size_t> slot;
+    for (size_t i = 0; i < n; ++i) {
+        if (h_positions[i] >> depth) return fail(ctx, SS_ERR_INVALID, "ss_dist_open: position out of range");
+        if ((int)(h_positions[i] >> sub_log) == d->rank) { local.push_back(h_positions[i] & ((1ull << sub_log) - 1)); slot.push_back(i); }
+    }
+    memset(h_paths, 0, n * (size_t)depth * 32);
+    if (!local.empty()) {
+        std::vector<uint8_t> low(local.size() * (size_t)sub_log * 32), top((size_t)log_w * 32);
+        if ((rc = ss_merkle_open(ctx, subtree, local.data(), local.size(), low.data()))) return rc;
+        if ((rc = ss_merkle_combine_open(ctx, kind, h_subroots, log_w, subroots_algebraic, (uint64_t)d->rank, top.data()))) return rc;
+        for (size_t k = 0; k < local.size(); ++k) {
+            uint8_t *out = h_paths + slot[k] * (size_t)depth * 32;
+            memcpy(out, low.data() + k * (size_t)sub_log * 32, (size_t)sub_log * 32);
+            memcpy(out + (size_t)sub_log * 32, top.data(), top.size());
+        }
+    }
+    return share_bytes(ctx, d, h_paths, n * (size_t)depth * 32, pick_stream(ctx, stream));
+}
+
+ss_status ss_dist_gather_rows(ss_ctx *ctx, const void *d_cols, uint64_t col_stride, int n_cols, int log_rows, const uint64_t *h_indices,
+                              size_t n, void *h_rows, void *stream) {
+    if (!ctx) return SS_ERR_INVALID;
+    Dist *d;
+    ss_status rc = get(ctx, &d);
+    if (rc) return rc;
+    if (!d_cols || n_cols < 1 || log_rows < 2 * d->log_w || (n && (!h_indices || !h_rows))) return fail(ctx, SS_ERR_INVALID, "ss_dist_gather_rows: bad arguments");
+    if (n == 0) return SS_OK;
+    const unsigned long long m = (1ull << log_rows) / d->world, s = m / d->world;
+    const size_t row_bytes = (size_t)n_cols * 32;
+    std::vector<uint64_t> mine;
+    std::vector<size_t> slot;
+    for (size_t i = 0; i < n; ++i) {
+        if (h_indices[i] >> log_rows) return fail(ctx, SS_ERR_INVALID, "ss_dist_gather_rows: row out of range");
+        if ((int)((h_indices[i] % m) / s) == d->rank) { mine.push_back(h_indices[i]); slot.push_back(i); }
+    }
+    uint8_t *out = static_cast<uint8_t *>(h_rows);
+    memset(out, 0, n * row_bytes);
+    if (!mine.empty()) {
+        std::vector<uint8_t> got(mine.size() * row_bytes);
+        if ((rc = ss_rows_gather(ctx, d_cols, col_stride, n_cols, mine.data(), mine.size(), got.data()))) return rc;
+        for (size_t k = 0; k < mine.size(); ++k) memcpy(out + slot[k] * row_bytes, got.data() + k * row_bytes, row_bytes);
+    }
+    return share_bytes(ctx, d, out, n * row_bytes, pick_stream(ctx, stream));
 }
 
 }  // extern "C"

@@ -10,6 +10,7 @@
 //
 // HBM traffic (algorithmic): leaves N*32*C read + N*32 written; nodes (N-1)*(64 read + 32 written).
 #include "ctx.h"
+#include <cstring>
 #include "hashes.cuh"
 #include "pedersen.cuh"
 
@@ -670,12 +671,11 @@ ss_status ss_merkle_open(ss_ctx *ctx, const ss_tree *tree, const uint64_t *h_ind
     return gather_virtual(ctx, tree, v, h_paths);
 }
 
-// Top of a row-sharded tree: `count` = 2^log_count sub-tree roots (storage form, byte-hash kinds) ->
-// root of the tree whose leaves they are.  Used when each GPU commits a row range.
-ss_status ss_merkle_combine(ss_ctx *ctx, ss_tree_kind kind, const uint8_t *h_subroots, int log_count, uint8_t root[32]) {
-    if (!ctx || !h_subroots || !root || log_count < 0 || log_count > 16) return SS_ERR_INVALID;
+// Top of a row-sharded tree: `count` = 2^log_count sub-tree roots (as ss_merkle_root returns them) -> the nodes of the
+// tree whose leaves they are, on the device: d[count .. 2 count) = the sub-roots as given, d[c .. 2c) the level of c nodes
+// in storage form, d[1] the root.  Used when each GPU commits a row range.  The caller dev_free()s *out.
+static ss_status combine_levels(ss_ctx *ctx, ss_tree_kind kind, const uint8_t *h_subroots, int log_count, uint8_t **out) {
     const unsigned long long count = 1ull << log_count;
-    if (log_count == 0) { for (int i = 0; i < 32; ++i) root[i] = h_subroots[i]; return SS_OK; }
     int bh, mask;
     byte_hash_of(kind, bh, mask);
     PedersenTable tab{nullptr};
@@ -686,7 +686,7 @@ ss_status ss_merkle_combine(ss_ctx *ctx, ss_tree_kind kind, const uint8_t *h_sub
         ss_status rc = pedersen_table(ctx, &tab);
         if (rc) return rc;
     }
-    uint8_t *d = nullptr;                       // nodes[count .. 2count) = sub-roots, nodes[1] = root
+    uint8_t *d = nullptr;
     SS_CUDA_CHECK(ctx, dev_alloc(ctx, reinterpret_cast<void **>(&d), 2 * count * 32));
     cudaMemcpy(d + 32 * count, h_subroots, count * 32, cudaMemcpyHostToDevice);
     for (int lvl = log_count - 1; lvl >= 0; --lvl) {
@@ -702,12 +702,56 @@ ss_status ss_merkle_combine(ss_ctx *ctx, ss_tree_kind kind, const uint8_t *h_sub
             });
         }
     }
+    *out = d;
+    return SS_OK;
+}
+
+ss_status ss_merkle_combine(ss_ctx *ctx, ss_tree_kind kind, const uint8_t *h_subroots, int log_count, uint8_t root[32]) {
+    if (!ctx || !h_subroots || !root || log_count < 0 || log_count > 16) return SS_ERR_INVALID;
+    if (log_count == 0) { for (int i = 0; i < 32; ++i) root[i] = h_subroots[i]; return SS_OK; }
+    uint8_t *d = nullptr;
+    ss_status rc = combine_levels(ctx, kind, h_subroots, log_count, &d);
+    if (rc) return rc;
     uint8_t raw[32];
     cudaError_t e = cudaMemcpy(raw, d + 32, 32, cudaMemcpyDeviceToHost);
     dev_free(ctx, d);
     if (e != cudaSuccess) return fail(ctx, SS_ERR_CUDA, "ss_merkle_combine: %s", cudaGetErrorString(e));
     if (kind == SS_TREE_FRIENDLY) felt_to_be_bytes(raw, root);
     else for (int i = 0; i < 32; ++i) root[i] = raw[i];
+    return SS_OK;
+}
+
+// The upper part of an authentication path through a row-sharded tree: the log_count siblings above sub-tree `index`, bottom
+// first, in the storage form ss_merkle_open uses (so that  ss_merkle_open(sub-tree) ++ this  is the path of the whole tree).
+ss_status ss_merkle_combine_open(ss_ctx *ctx, ss_tree_kind kind, const uint8_t *h_subroots, int log_count, int subroots_algebraic,
+                                 uint64_t index, uint8_t *h_path) {
+    if (!ctx || !h_subroots || (!h_path && log_count) || log_count < 0 || log_count > 16 || index >> log_count) return SS_ERR_INVALID;
+    if (log_count == 0) return SS_OK;
+    const unsigned long long count = 1ull << log_count;
+    uint8_t *d = nullptr;
+    ss_status rc = combine_levels(ctx, kind, h_subroots, log_count, &d);
+    if (rc) return rc;
+    std::vector<uint8_t> nodes(2 * count * 32);
+    cudaError_t e = cudaMemcpy(nodes.data(), d, nodes.size(), cudaMemcpyDeviceToHost);
+    dev_free(ctx, d);
+    if (e != cudaSuccess) return fail(ctx, SS_ERR_CUDA, "ss_merkle_combine_open: %s", cudaGetErrorString(e));
+    unsigned long long pos = count + index;
+    for (int k = 0; k < log_count; ++k, pos >>= 1) {
+        const uint8_t *sib = nodes.data() + 32 * (pos ^ 1ull);
+        uint8_t *out = h_path + 32 * k;
+        if (k == 0 && kind == SS_TREE_FRIENDLY && subroots_algebraic) {
+            // a Pedersen sub-root came in as its big-endian canonical integer: back to Montgomery limbs
+            Fp v;
+            for (int w = 0; w < 8; ++w)
+                v.l[7 - w] = ((uint32_t)sib[4 * w] << 24) | ((uint32_t)sib[4 * w + 1] << 16) | ((uint32_t)sib[4 * w + 2] << 8) | (uint32_t)sib[4 * w + 3];
+            const Fp m = fp::canon(fp::mul(v, fp::r2()));
+            for (int i = 0; i < 8; ++i) {
+                out[4 * i] = (uint8_t)m.l[i]; out[4 * i + 1] = (uint8_t)(m.l[i] >> 8); out[4 * i + 2] = (uint8_t)(m.l[i] >> 16); out[4 * i + 3] = (uint8_t)(m.l[i] >> 24);
+            }
+        } else {
+            memcpy(out, sib, 32);
+        }
+    }
     return SS_OK;
 }
 

@@ -227,6 +227,7 @@ class HotPathProver:
             subs = gather_subroots(bytes(root), world, self.device)
             buf = (ctypes.c_uint8 * (32 * world)).from_buffer_copy(b"".join(subs))
             c.check(c.lib.ss_merkle_combine(c.handle, opt.tree_kind, buf, world.bit_length() - 1, root))
+        self._last_subroots = b"".join(subs) if shard else None         # (None: this rank holds the whole tree)
         return bytes(root), handle
 
     def _remainder(self, evals: torch.Tensor, log_blowup: int) -> np.ndarray:
@@ -258,7 +259,7 @@ class HotPathProver:
         opt, L = self.opt, self.layout
         assert base.num_cols == L.num_base_columns and base.num_rows == self.n
         if self.world > 1:
-            return self._prove_sharded(base, ext, hints, column_ready)
+            return self._prove_sharded(base, ext, hints, column_ready, queries, keep_openings)
         coin = self.coin
         res = HotPathResult()
         dev = self.device
@@ -438,13 +439,14 @@ class HotPathProver:
         return res
 
     # ---- the device stages over several GPUs: every transform row-sharded (parallel.ShardedTransforms) ---------------------
-    def _commit_pieces(self, cols: torch.Tensor, col_stride: int, log_rows: int) -> bytes:
+    def _commit_pieces(self, cols: torch.Tensor, col_stride: int, log_rows: int):
         """Commitment of a block-cyclic matrix in the reference's (bit-reversed) leaf order.  A rank owns contiguous row
         ranges, but tree leaf p commits row brev(p), so a rank's rows are spread over the whole tree: every rank hashes the
         rows it owns, the 32-byte leaf digests are redistributed with one all-to-all (row i goes to the rank that owns leaf
         brev(i), i.e. brev_W(i mod W): 1/n_cols of the matrix traffic), each rank builds the sub-tree over its contiguous
         range of N / W leaves, and the W sub-roots are all-gathered and combined (ss_merkle_combine; Pedersen levels for
-        the Friendly tree).  A single-column matrix is committed with raw leaves (the elements themselves travel)."""
+        the Friendly tree).  A single-column matrix is committed with raw leaves (the elements themselves travel).
+        Returns (root, this rank's sub-tree handle, the W sub-roots): what _open_sharded needs for the query phase."""
         import torch.distributed as dist
 
         from .parallel import _all_to_all, pieces
@@ -479,13 +481,75 @@ class HotPathProver:
                                                       ctypes.byref(handle), None))
         root = (ctypes.c_uint8 * 32)()
         c.check(c.lib.ss_merkle_root(c.handle, handle, root))
-        c.lib.ss_tree_free(handle)
         from .parallel import gather_subroots
 
         subs = gather_subroots(bytes(root), W, self.device)
         buf = (ctypes.c_uint8 * (32 * W)).from_buffer_copy(b"".join(subs))
         c.check(c.lib.ss_merkle_combine(c.handle, opt.tree_kind, buf, log_w, root))
-        return bytes(root)
+        return bytes(root), handle, b"".join(subs)
+
+    def _open_sharded(self, handle, subroots, log_rows: int, n_cols: int, positions) -> np.ndarray:
+        """MerkleTree::prove for leaf positions of a tree whose leaves are split into W contiguous ranges (one sub-tree per rank):
+        the owner of a position opens its sub-tree and appends the siblings above its sub-root (ss_merkle_combine_open); the paths
+        are then shared so that every rank holds uint8[q, log_rows, 32] exactly as ss_merkle_open on one GPU returns it.
+        subroots None: every rank holds the whole tree (small FRI layers)."""
+        import torch.distributed as dist
+
+        c, opt, W, r = self.ctx, self.opt, self.world, self.rank
+        u64p, u8p = ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint8)
+        q = len(positions)
+        paths = np.zeros((q, log_rows, 32), dtype=np.uint8)
+        if subroots is None:
+            idx = np.array(positions, dtype=np.uint64)
+            c.check(c.lib.ss_merkle_open(c.handle, handle, idx.ctypes.data_as(u64p), q, paths.ctypes.data_as(u8p)))
+            return paths
+        log_w = W.bit_length() - 1
+        sub_log = log_rows - log_w
+        algebraic = int(opt.tree_kind == _lib.TREE_FRIENDLY and (n_cols == 1 or log_w < opt.n_friendly))
+        buf = (ctypes.c_uint8 * len(subroots)).from_buffer_copy(subroots)
+        if opt.capi_collectives:
+            idx = np.array(positions, dtype=np.uint64)
+            c.check(c.lib.ss_dist_open(c.handle, opt.tree_kind, algebraic, handle, buf, idx.ctypes.data_as(u64p), q, paths.ctypes.data_as(u8p), None))
+            return paths
+        mine = [k for k, p in enumerate(positions) if p >> sub_log == r]
+        if mine:
+            idx = np.array([positions[k] & ((1 << sub_log) - 1) for k in mine], dtype=np.uint64)
+            low = np.zeros((len(mine), sub_log, 32), dtype=np.uint8)
+            c.check(c.lib.ss_merkle_open(c.handle, handle, idx.ctypes.data_as(u64p), len(mine), low.ctypes.data_as(u8p)))
+            top = np.zeros((log_w, 32), dtype=np.uint8)
+            c.check(c.lib.ss_merkle_combine_open(c.handle, opt.tree_kind, buf, log_w, algebraic, r, top.ctypes.data_as(u8p)))
+            paths[mine, :sub_log] = low
+            paths[mine, sub_log:] = top
+        t = torch.from_numpy(paths).to(self.device)
+        dist.all_reduce(t)                                   # one contributor per entry: the sum is the value
+        return t.cpu().numpy()
+
+    def _read_rows_sharded(self, cols: torch.Tensor, col_stride: int, log_rows: int, rows) -> np.ndarray:
+        """Matrix::read_row of a block-cyclic matrix: the rank that owns natural row i reads it, then the rows are shared.
+        -> uint64[q, n_cols, 4] on every rank."""
+        import torch.distributed as dist
+
+        c, W, r = self.ctx, self.world, self.rank
+        n_cols, q = cols.shape[0], len(rows)
+        out = np.zeros((q, n_cols, 4), dtype=np.uint64)
+        u64p = ctypes.POINTER(ctypes.c_uint64)
+        if self.opt.capi_collectives:
+            idx = np.array(rows, dtype=np.uint64)
+            c.check(c.lib.ss_dist_gather_rows(c.handle, ctypes.c_void_p(cols.data_ptr()), col_stride, n_cols, log_rows, idx.ctypes.data_as(u64p), q,
+                                              out.ctypes.data_as(ctypes.c_void_p), None))
+            return out
+        m = (1 << log_rows) // W
+        s = m // W
+        mine = [k for k, i in enumerate(rows) if (i % m) // s == r]
+        if mine:
+            idx = np.array([rows[k] for k in mine], dtype=np.uint64)
+            got = np.zeros((len(mine), n_cols, 4), dtype=np.uint64)
+            c.check(c.lib.ss_rows_gather(c.handle, ctypes.c_void_p(cols.data_ptr()), col_stride, n_cols, idx.ctypes.data_as(u64p), len(mine),
+                                         got.ctypes.data_as(ctypes.c_void_p)))
+            out[mine] = got
+        t = torch.from_numpy(out.view(np.int64)).to(self.device)
+        dist.all_reduce(t)
+        return t.cpu().numpy().view(np.uint64)
 
     def _lde_pipes(self, dev, W, rank):
         """two (stream, ShardedTransforms) pairs, each with its own context (scratch buffers and work-buffer pool are per context
@@ -536,7 +600,7 @@ class HotPathProver:
             req.wait()
         del staged
 
-    def _prove_sharded(self, base: Matrix, ext, hints, column_ready) -> HotPathResult:
+    def _prove_sharded(self, base: Matrix, ext, hints, column_ready, queries: bool = True, keep_openings: bool = False) -> HotPathResult:
         """world > 1 (torch.distributed initialised, one process per GPU).  Every column's transforms are split over the
         ranks (parallel.ShardedTransforms: two all-to-alls per LDE column, 1/W of the arithmetic per rank whatever the
         number of columns); each rank ends up with W contiguous row ranges ("pieces") of EVERY column, on which it hashes
@@ -585,13 +649,18 @@ class HotPathProver:
             else:
                 self._exchange_halo(cols, log_N, halo)
 
+        trace_trees = []                                  # (sub-tree handle, sub-roots, columns) of base / ext / composition
+
         def commit(cols):
             if capi:
-                root = (ctypes.c_uint8 * 32)()
+                root, sub, subs = (ctypes.c_uint8 * 32)(), ctypes.c_void_p(), (ctypes.c_uint8 * (32 * W))()
                 c.check(c.lib.ss_dist_commit(c.handle, opt.tree_kind, opt.n_friendly, ctypes.c_void_p(cols.data_ptr()), S, cols.shape[0], log_N,
-                                             root, _stream_ptr()))
-                return bytes(root)
-            return self._commit_pieces(cols, S, log_N)
+                                             root, ctypes.byref(sub), subs, _stream_ptr()))
+                root, subs = bytes(root), bytes(subs)
+            else:
+                root, sub, subs = self._commit_pieces(cols, S, log_N)
+            trace_trees.append((sub, subs, cols))
+            return root
 
         self.mark("start")
         S = N + opt.col_pad_rows
@@ -750,7 +819,7 @@ class HotPathProver:
             nxt = fri_fold(evals, opt.log_fold, _mont(fri_alpha), _mont(offset), starkware_scale=True, ctx=c, rows=(lo, cnt) if shard else None)
             if shard:
                 self._gather_rows(nxt, lo, cnt)
-            layers.append(handle)
+            layers.append((handle, self._last_subroots, evals, log_size))
             evals, log_size, offset = nxt, log_size - opt.log_fold, pow(offset, 1 << opt.log_fold, P)
         self.final_domain = (log_size, offset)
         res.remainder = self._remainder(evals, b)
@@ -759,8 +828,35 @@ class HotPathProver:
         if opt.grinding_factor:
             res.pow_nonce = coin.grind_proof_of_work(opt.grinding_factor, c)
             coin.reseed_with_int(res.pow_nonce)
-        for handle in layers:
+        if queries:
+            # 15: query phase.  Leaf p of a trace tree commits LDE row brev(p): the leaf's owner (contiguous leaf ranges) opens
+            # the path, the row's owner (block-cyclic pieces) reads the values; both are shared, so every rank ends with the openings.
+            pos = res.query_positions = coin.draw_queries(opt.num_queries, N)
+            nat = [_brev(p, log_N) for p in pos]
+            for name, (sub, subs, cols) in zip(("base", "ext", "composition"), trace_trees):
+                paths = self._open_sharded(sub, subs, log_N, cols.shape[0], pos)
+                rows_out = self._read_rows_sharded(cols, S, log_N, nat)
+                res.opened_bytes += paths.nbytes + rows_out.nbytes
+                if keep_openings:
+                    res.trace_queries[name] = {"rows": rows_out, "paths": paths}
+            F = 1 << opt.log_fold
+            col_perm = [_brev(j, opt.log_fold) for j in range(F)]
+            for handle, subs, layer_evals, ls in layers:
+                log_rows = ls - opt.log_fold
+                pos = sorted({p >> opt.log_fold for p in pos})
+                paths = self._open_sharded(handle, subs, log_rows, F, pos)
+                res.opened_bytes += paths.nbytes
+                if keep_openings:                        # (every rank holds the whole layer: no exchange for the values)
+                    idx = np.array([_brev(r, log_rows) for r in pos], dtype=np.uint64)
+                    rows_out = np.zeros((len(idx), F, 4), dtype=np.uint64)
+                    c.check(c.lib.ss_rows_gather(c.handle, ctypes.c_void_p(layer_evals.data_ptr()), 1 << log_rows, F,
+                                                 idx.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), len(idx), rows_out.ctypes.data_as(ctypes.c_void_p)))
+                    res.fri_layers.append({"positions": pos, "rows": np.ascontiguousarray(rows_out[:, col_perm]), "paths": paths})
+            self.mark("queries")
+        for handle, _, _, _ in layers:
             c.lib.ss_tree_free(handle)
+        for sub, _, _ in trace_trees:
+            c.lib.ss_tree_free(sub)
         return res
 
     def stage_ms(self) -> dict:

@@ -1,5 +1,6 @@
 """GPU, needs >= 2 devices (skipped on a one-GPU box): the row-sharded hot path over NCCL reproduces the single-GPU
-commitments, out-of-domain values, FRI roots and remainder bit for bit (tools/check_multi_gpu.py under torchrun)."""
+commitments, out-of-domain values, FRI roots, remainder and query openings (rows + authentication paths of every trace tree
+and FRI layer) bit for bit (tools/check_multi_gpu.py under torchrun)."""
 import os
 import subprocess
 import sys
