@@ -101,6 +101,13 @@ ss_status ss_lde(ss_ctx *ctx, ss_field field, const void *d_trace, uint64_t trac
                  int log_n, int log_blowup, void *d_lde, uint64_t lde_stride, void *d_coeffs,
                  uint64_t coeff_stride, ss_order out_order, void *stream);
 
+/* ss_coset_eval: the polynomials whose coefficients ss_lde left in d_coeffs (coefficient k at position brev(k), scaled or
+ * not) evaluated on the coset h<w_n>: dst[j] = sum_k coeff_k h^k w_n^(j k), natural order.  With ss_lde's c_k 3^k and
+ * h = z/3 this yields T(z g^j) for every j: all out-of-domain mask values of a column (ministark's OOD evaluation of
+ * air.trace_arguments()) from one transform.  d_dst may equal d_coeffs. */
+ss_status ss_coset_eval(ss_ctx *ctx, ss_field field, const void *d_coeffs, uint64_t coeff_stride, int n_cols, int log_n,
+                        const void *h_h, void *d_dst, uint64_t dst_stride, void *stream);
+
 /* ------------------------------------------------------------------ Merkle (§8 a9-a13)
  * ss_merkle_build = MatrixMerkleTree::from_matrix (crypto/src/merkle/mod.rs:110-123, :289-304):
  * n_cols == 1 -> raw-leaf variant, n_cols >= 2 -> row hashes (crypto/src/merkle/utils.rs:19-46)

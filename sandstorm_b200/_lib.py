@@ -43,6 +43,7 @@ SIGNATURES = {
     "ss_merkle_nodes": (c_int, [c_void_p, c_void_p, POINTER(c_uint64), c_size_t, POINTER(c_uint8)]),
     "ss_merkle_leaves": (c_int, [c_void_p, c_void_p, POINTER(c_uint64), c_size_t, POINTER(c_uint8)]),
     "ss_merkle_open": (c_int, [c_void_p, c_void_p, POINTER(c_uint64), c_size_t, POINTER(c_uint8)]),
+    "ss_coset_eval": (c_int, [c_void_p, c_int, c_void_p, c_uint64, c_int, c_int, c_void_p, c_void_p, c_uint64, c_void_p]),
     "ss_merkle_combine": (c_int, [c_void_p, c_int, POINTER(c_uint8), c_int, POINTER(c_uint8)]),
     "ss_merkle_combine_open": (c_int, [c_void_p, c_int, POINTER(c_uint8), c_int, c_int, c_uint64, POINTER(c_uint8)]),
     "ss_tree_log_rows": (c_int, [c_void_p]),

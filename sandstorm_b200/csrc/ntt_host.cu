@@ -93,6 +93,10 @@ ss_status custom_scale(ss_ctx *ctx, int log_len, const Fp &c, const Fp &h, const
     const size_t n = (size_t)1 << log_len, n_lo = n < 4096 ? n : 4096, n_hi = n <= 4096 ? 1 : n / 4096;
     auto it = ctx->scale_tables.find(key);
     if (it == ctx->scale_tables.end()) {
+        if (ctx->scale_tables.size() >= 48) {       // per-proof scales (ss_coset_eval at z/3) would pile up: start over
+            for (auto &kv : ctx->scale_tables) cudaFree(kv.second.first);      // (cudaFree waits for kernels still reading them)
+            ctx->scale_tables.clear();
+        }
         std::vector<Fp> host(n_lo + n_hi);
         geometric(host.data(), n_lo, c, h);
         geometric(host.data() + n_lo, n_hi, fp::one(), fp::pow_u64(h, 4096));
@@ -404,6 +408,33 @@ ss_status ss_ntt_shard(ss_ctx *ctx, ss_field field, const void *d_src, uint64_t 
         if ((rc = run_ntt(ctx, fwd, st))) return rc;
     }
     return SS_OK;
+}
+
+/* Evaluations of polynomials on an arbitrary coset h<w_n> from the coefficient vectors ss_lde leaves behind (d_coeffs:
+ * coefficient k, possibly pre-scaled, at position brev(k)):  dst[j] = sum_k coeff_k * h^k * w_n^(j k), natural order —
+ * one forward transform with the scale fused into its first pass.  With ss_lde's coset-scaled coefficients (c_k 3^k) and
+ * h = z / 3 this is T(z g^j) for EVERY j at once: the out-of-domain mask values of a column with many taps
+ * (air.trace_arguments(): up to 105 offsets of one column in the starknet layout) for the price of one NTT instead of one
+ * n-term sum per tap.  d_dst may equal d_coeffs. */
+ss_status ss_coset_eval(ss_ctx *ctx, ss_field field, const void *d_coeffs, uint64_t coeff_stride, int n_cols, int log_n, const void *h_h,
+                        void *d_dst, uint64_t dst_stride, void *stream) {
+    if (!ctx) return SS_ERR_INVALID;
+    if (field != SS_FIELD_FP252) return fail(ctx, SS_ERR_UNSUPPORTED, "ss_coset_eval: field %d not built", (int)field);
+    if (!d_coeffs || !d_dst || !h_h || n_cols < 0 || log_n < 1 || log_n > 40 || coeff_stride < (1ull << log_n) || dst_stride < (1ull << log_n))
+        return fail(ctx, SS_ERR_INVALID, "ss_coset_eval: bad arguments");
+    if (n_cols == 0) return SS_OK;
+    SS_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+    Fp h;
+    memcpy(h.l, h_h, 32);
+    NttJob fwd{};
+    fwd.dst = static_cast<Fp *>(d_dst); fwd.src = static_cast<const Fp *>(d_coeffs);
+    fwd.dst_stride = dst_stride; fwd.src_stride = coeff_stride;
+    fwd.n_cols = n_cols; fwd.log_n = log_n; fwd.inverse = false; fwd.dit = true;
+    fwd.canon_out = true;
+    fwd.pre_scale = SCALE_TABLE_BREV;
+    ss_status rc = custom_scale(ctx, log_n, fp::one(), fp::canon(h), &fwd.sc_lo, &fwd.sc_hi);
+    if (rc) return rc;
+    return run_ntt(ctx, fwd, pick_stream(ctx, stream));
 }
 
 /* The size-W transform across the W ranks of a sharded NTT (W = 2^log_w <= 8):

@@ -70,6 +70,9 @@ class ProofOptions:
     tree_kind: int = _lib.TREE_KECCAK_M20        # src/claims.rs:18-21 (starknet / EthVerifier); recursive claims use TREE_FRIENDLY
     n_friendly: int = 22                         # NUM_FRIENDLY_COMMITMENT_LAYERS, src/claims.rs:10 (TREE_FRIENDLY only)
     col_pad_rows: int = 0                        # padding between the columns of the working matrix (not a protocol parameter)
+    ood_transform_min_taps: int = 32             # a column with at least this many mask offsets gets its out-of-domain values from ONE
+                                                 # transform onto the coset z<g> (ss_coset_eval) instead of one n-term sum per offset;
+                                                 # same values either way (world = 1 only; 0 disables)
 
 
 class SeededCoin:
@@ -277,10 +280,19 @@ class HotPathProver:
             for j in range(src.num_cols):
                 if column_ready is not None:
                     column_ready(first_col + j)          # e.g. make the stream wait for the upload of this column
+                keep = None
+                if first_col + j in heavy:               # interpolated polynomial (c_k 3^k, bit-reversed) kept for the OOD stage
+                    keep = coeffs_of[first_col + j] = torch.empty((n, 4), dtype=torch.int64, device=dev)
                 c.check(c.lib.ss_lde(c.handle, _lib.FIELD_FP252, ctypes.c_void_p(src.data[j].data_ptr()), src.col_stride, 1, self.log_n, b,
-                                     ctypes.c_void_p(lde[first_col + j].data_ptr()), S, None, n,
+                                     ctypes.c_void_p(lde[first_col + j].data_ptr()), S, ctypes.c_void_p(keep.data_ptr()) if keep is not None else None, n,
                                      _lib.ORDER_NATURAL, None))
 
+        taps = L.taps()
+        per_col = {}
+        for col, _ in taps:
+            per_col[col] = per_col.get(col, 0) + 1
+        heavy = {col for col, cnt in per_col.items() if opt.ood_transform_min_taps and cnt >= opt.ood_transform_min_taps and self.log_n >= 1}
+        coeffs_of = {}
         # 3-5: base trace
         lde_cols(base, 0)
         self.mark("lde_base")
@@ -333,14 +345,29 @@ class HotPathProver:
         #     weight vector, ss_ood_eval)
         coin.reseed_with_digest(res.roots["composition"])
         z = res.ood_point = coin.draw()
-        taps = L.taps()
         if column_ready is not None:
             column_ready(None)                           # every trace column is read from here on
         parts = np.zeros((len(taps), 4), dtype=np.uint64)
         for mat, first, count in ((base, 0, nb), (ext, nb, C - nb)):
-            idx = [k for k, (col, _) in enumerate(taps) if first <= col < first + count]
+            idx = [k for k, (col, _) in enumerate(taps) if first <= col < first + count and col not in heavy]
             if idx:
                 parts[idx] = ood_eval(mat, [taps[k][0] - first for k in idx], [taps[k][1] for k in idx], _mont(z))
+        if heavy:
+            # columns with many offsets: T(z g^j) for every j from one transform of the kept coefficients (h = z / 3 undoes the
+            # coset scaling ss_lde left on them), then the mask offsets are read out of it
+            on_z = torch.empty((n, 4), dtype=torch.int64, device=dev)
+            h_scale = _mont(z * pow(3, -1, P) % P)
+            for col in sorted(heavy):
+                c.check(c.lib.ss_coset_eval(c.handle, _lib.FIELD_FP252, ctypes.c_void_p(coeffs_of[col].data_ptr()), n, 1, self.log_n,
+                                            h_scale.ctypes.data_as(ctypes.c_void_p), ctypes.c_void_p(on_z.data_ptr()), n, None))
+                idx = [k for k, (tc, _) in enumerate(taps) if tc == col]
+                rows_at = np.array([taps[k][1] % n for k in idx], dtype=np.uint64)
+                got = np.zeros((len(idx), 1, 4), dtype=np.uint64)
+                c.check(c.lib.ss_rows_gather(c.handle, ctypes.c_void_p(on_z.data_ptr()), n, 1, rows_at.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)),
+                                             len(idx), got.ctypes.data_as(ctypes.c_void_p)))
+                parts[idx] = got[:, 0]
+            del on_z
+            coeffs_of.clear()
         to_int = lambda a: [int(r[0]) | int(r[1]) << 64 | int(r[2]) << 128 | int(r[3]) << 192 for r in a]
         ood_m = to_int(parts)
         zc = pow(z, self.ce, P)

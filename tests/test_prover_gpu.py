@@ -148,3 +148,30 @@ def test_barycentric_ood_matches_horner(ss, oracle, log_n):
         cuts = [0, n // 8, n // 2 + 1, n]
         parts = [oracle.from_mont(ood_eval(m, [c for c, _ in taps], [off for _, off in taps], zm, rows=(a, b - a))) for a, b in zip(cuts, cuts[1:])]
         assert [sum(v) % P for v in zip(*parts)] == want
+
+
+def test_ood_values_do_not_depend_on_how_they_are_computed(ss, oracle):
+    """out-of-domain mask values from per-tap barycentric sums (ood_transform_min_taps=0) == from one coset transform per
+    column (ss_coset_eval; min_taps=1 sends every column that way) == Horner on the oracle's interpolation."""
+    import torch
+
+    from sandstorm_b200.prover import HotPathProver, ProofOptions
+
+    P, log_n = oracle.P, 11
+    rng = np.random.default_rng(5)
+    got = {}
+    for min_taps in (0, 1, 20):
+        hp = HotPathProver("recursive", log_n, ProofOptions(num_queries=4, ood_transform_min_taps=min_taps))
+        L = hp.layout
+        if not got:
+            base = oracle.random_felts(rng, L.num_base_columns, 1 << log_n)
+            ext = oracle.random_felts(rng, L.num_extension_columns, 1 << log_n)
+        res = hp.prove(ss.Matrix.from_numpy(base), ss.Matrix.from_numpy(ext), queries=False)
+        torch.cuda.synchronize()
+        got[min_taps] = (res.ood_point, list(res.ood_trace), res.fri_roots)
+    assert got[0] == got[1] == got[20]
+    coeffs = [oracle.from_mont(c) for c in oracle.ntt(np.concatenate([base, ext]), inverse=True)]
+    g, z = pow(3, (P - 1) >> log_n, P), got[1][0]
+    for k, (col, off) in enumerate(L.taps()):
+        if k % 7 == 0:
+            assert got[1][1][k] == sum(v * pow(z * pow(g, off, P) % P, e, P) for e, v in enumerate(coeffs[col])) % P
