@@ -72,7 +72,7 @@ class ProofOptions:
     col_pad_rows: int = 0                        # padding between the columns of the working matrix (not a protocol parameter)
     ood_transform_min_taps: int = 32             # a column with at least this many mask offsets gets its out-of-domain values from ONE
                                                  # transform onto the coset z<g> (ss_coset_eval) instead of one n-term sum per offset;
-                                                 # same values either way (world = 1 only; 0 disables)
+                                                 # same values either way (0 disables)
 
 
 class SeededCoin:
@@ -784,8 +784,29 @@ class HotPathProver:
         to_int = lambda a: [int(r[0]) | int(r[1]) << 64 | int(r[2]) << 128 | int(r[3]) << 192 for r in a]
         rinv = pow(R, -1, P)
         acc = [0] * len(taps)
+        per_col = {}
+        for col, _ in taps:
+            per_col[col] = per_col.get(col, 0) + 1
+        heavy = {col for col, cnt in per_col.items() if opt.ood_transform_min_taps and cnt >= opt.ood_transform_min_taps}
+        if heavy:
+            # tap-heavy columns: T(z g^j) for every j by one more sharded transform pair (coefficients scaled by z^k, then the
+            # forward transform without expansion); the mask offsets are then read from their owners.  Same values as the sums.
+            on_z = torch.empty((n, 4), dtype=torch.int64, device=dev)
+            ninv = pow(n, -1, P)
+            for col in sorted(heavy):
+                src = base.data[col] if col < nb else ext.data[col - nb]
+                share = st.to_coefficients(src, log_n, ninv * pow(z, rank, P) % P, pow(z, W, P))
+                st.from_coefficients(share, log_n - (W.bit_length() - 1), 0, on_z)
+                idx = [k for k, (tc, _) in enumerate(taps) if tc == col]
+                vals = to_int(self._read_rows_sharded(on_z.view(1, n, 4), n, log_n, [taps[k][1] % n for k in idx])[:, 0])
+                if rank == 0:                             # (final values, not partial sums: counted once)
+                    for k, v in zip(idx, vals):
+                        acc[k] = v
+            del on_z
         for mat, first, count in ((base, 0, nb), (ext, nb, C - nb)):
-            idx = [k for k, (col, _) in enumerate(taps) if first <= col < first + count]
+            idx = [k for k, (col, _) in enumerate(taps) if first <= col < first + count and col not in heavy]
+            if not idx:
+                continue
             for lo, cnt in Pn:
                 part = to_int(ood_eval(mat, [taps[k][0] - first for k in idx], [taps[k][1] for k in idx], _mont(z), rows=(lo, cnt)))
                 for k, v in zip(idx, part):
