@@ -42,6 +42,8 @@ CE = 2                                      # air.ce_blowup_factor() for Cairo (
 CYCLE_HEIGHT_LOG = 4                        # n = 16 * n_steps (layouts/src/*/mod.rs CYCLE_HEIGHT)
 WORKLOADS = {"starknet22": ("starknet", 22, "keccak_m20"), "recursive20": ("recursive", 20, "friendly")}
 MUL_PEAK = 592 * 1.965e9 / 275 * 32         # Fp252 multiplications/s if the IMAD pipe did nothing else (tools/ubench/bfly.cu)
+MUL_SUSTAINED = 592 * 1.965e9 / 355 * 32    # what a register-only loop of dependent fp::mul sustains with every warp timed to completion
+                                            # (tools/ubench/mulmix.cu, profiles/r03_mul_variants.md): the practical ceiling of the routine
 
 
 def workload_name(layout: str, log_n: int, tree: str, n_base: int, n_ext: int) -> str:
@@ -468,6 +470,7 @@ def gpu_arm(args):
                     "frac": ce_ach / peak, "traffic": ce_traffic, "peak_source": peak_src, "launch_ms": ce_ms,
                     "algorithmic_bytes_per_row": 32 * (n_cols_read + 1),
                     "field_muls_per_s": muls, "field_mul_pipe_peak_per_s": MUL_PEAK, "field_mul_pipe_frac": muls / MUL_PEAK,
+                    "field_mul_sustained_per_s": MUL_SUSTAINED, "field_mul_sustained_frac": muls / MUL_SUSTAINED,
                     "note": "arithmetic-bound: %d Montgomery multiplications + %d add/sub per row on %d algorithmic bytes; the integer pipe, not HBM, is the roof "
                             "(mul peak = 592 SMSPs x 1.965 GHz / 275 cycles per warp-multiplication, profiles/r01_ntt_tile_ab.md)" % (prog.n_mul, prog.n_addsub, 32 * (n_cols_read + 1))}
     cpu = None
