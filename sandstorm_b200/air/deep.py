@@ -121,3 +121,58 @@ def deep_expr_symbolic(taps, n_comp: int, first_comp_col: int, u_col: int, v_col
         q = (comp - comp_y) * Trace(v_col, 0)
         total = q if total is None else total + q
     return total
+
+
+def deep_expr_filtered(taps, n_comp: int, first_comp_col: int, u_col: int, v_col: int, g: int, p: int, filter_cols: dict, value_col: int) -> Expr:
+    """deep_expr_symbolic with the long sums taken out of the per-row program.  In the by-column form
+
+        deep(x) = sum_c T_c(x) W_c(x) - V(x) + (composition part),
+        W_c(x) = sum_{t in c} a_t / (x - z g^off_t),      V(x) = sum_t a_t y_t / (x - z g^off_t),
+
+    W_c and V are sums of simple poles on z<g>.  On the evaluation coset every x has the same x^n = K, so
+    1 / (x - zeta) = sum_k x^k zeta^(n-1-k) / (K - z^n) there: each of them is a POLYNOMIAL on the coset, whose n values cost two
+    size-n transforms whatever the number of poles (prover.py `_pole_sum_on_coset`).  filter_cols: {trace column: working column
+    that holds W_c on the coset rows} for the columns with many taps; value_col: the working column that holds V.  The columns
+    with few taps keep their shifted reads of u.  Same polynomial, hence the same values as deep_expr_symbolic."""
+    from .expr import Challenge
+
+    alpha = Challenge(0)
+    per_col: dict[int, Expr] = {}
+    k = 0
+    for col, off in taps:
+        if col not in filter_cols:
+            term = alpha.pow(k) * Constant(pow(g, -off, p)) * Trace(u_col, -off)
+            per_col[col] = term if col not in per_col else per_col[col] + term
+        k += 1
+    total = None
+    for col, a in per_col.items():
+        q = Trace(col, 0) * a
+        total = q if total is None else total + q
+    for col in sorted(filter_cols):
+        q = Trace(col, 0) * Trace(filter_cols[col], 0)
+        total = q if total is None else total + q
+    total = total - Trace(value_col, 0)
+    from .expr import Hint
+
+    comp, comp_y = None, None
+    for j in range(n_comp):
+        coeff = alpha.pow(k)
+        term = coeff * Trace(first_comp_col + j, 0)
+        comp = term if comp is None else comp + term
+        cy = coeff * Hint(k)
+        comp_y = cy if comp_y is None else comp_y + cy
+        k += 1
+    if comp is not None:
+        total = total + (comp - comp_y) * Trace(v_col, 0)
+    return total
+
+
+DEEP_FILTER_MIN_TAPS = 40      # one transform pair costs about as much as 37 taps of the per-row form (prover.ProofOptions default)
+
+
+def deep_filter_columns(taps, min_taps: int) -> list:
+    """the trace columns whose W_c goes through a transform (at least min_taps mask offsets), in ascending order"""
+    count: dict[int, int] = {}
+    for col, _ in taps:
+        count[col] = count.get(col, 0) + 1
+    return sorted(col for col, c in count.items() if min_taps and c >= min_taps)

@@ -38,7 +38,7 @@ import torch
 from . import _lib
 from .air import compile_program, compile_template
 from .air.program import tap_reach
-from .air.deep import deep_expr_shifted, deep_expr_symbolic, deep_terms
+from .air.deep import DEEP_FILTER_MIN_TAPS, deep_expr_filtered, deep_expr_shifted, deep_expr_symbolic, deep_filter_columns, deep_terms
 from .air.evaluate import evaluate
 from .air.expr import P
 from .air.layouts import load_layout
@@ -70,6 +70,10 @@ class ProofOptions:
     tree_kind: int = _lib.TREE_KECCAK_M20        # src/claims.rs:18-21 (starknet / EthVerifier); recursive claims use TREE_FRIENDLY
     n_friendly: int = 22                         # NUM_FRIENDLY_COMMITMENT_LAYERS, src/claims.rs:10 (TREE_FRIENDLY only)
     col_pad_rows: int = 0                        # padding between the columns of the working matrix (not a protocol parameter)
+    deep_filter_min_taps: int = DEEP_FILTER_MIN_TAPS   # DEEP quotient: a column with at least this many mask offsets gets its sum of
+                                                 # poles W_c(x) = sum_t a_t / (x - z g^off_t) — and the layout its V(x) when it has that many
+                                                 # distinct offsets — from two size-n transforms instead of one multiply-add per pole per row
+                                                 # (air/deep.py deep_expr_filtered; same values; world = 1 only; 0 disables)
     ood_transform_min_taps: int = 32             # a column with at least this many mask offsets gets its out-of-domain values from ONE
                                                  # transform onto the coset z<g> (ss_coset_eval) instead of one n-term sum per offset;
                                                  # same values either way (0 disables)
@@ -136,6 +140,16 @@ class HotPathProver:
         # columns of the working matrix: trace | composition (ce) | w = 1/(x-1) | u = 1/(x-z) | v = 1/(x-z^ce)
         C = self.layout.num_columns
         self.comp_col, self.w_col, self.u_col, self.v_col = C, C + self.ce, C + self.ce + 1, C + self.ce + 2
+        # ... | V | W_c of the tap-heavy columns   (only when the DEEP quotient takes its pole sums from transforms)
+        self.n_work_cols = C + self.ce + 3
+        self.value_col, self.filter_cols = None, {}
+        taps = self.layout.taps()
+        mt = self.opt.deep_filter_min_taps
+        if world == 1 and mt and log_n >= 1 and (deep_filter_columns(taps, mt) or len({off for _, off in taps}) >= mt):
+            self.value_col = self.n_work_cols
+            self.filter_cols = {col: self.value_col + 1 + j for j, col in enumerate(deep_filter_columns(taps, mt))}
+            self.n_work_cols += 1 + len(self.filter_cols)
+        self._deep_template_direct = None
         self._template = self._deep_template = None
         self._composition_program = None
         self._challenges = self._hints = self._alpha = None
@@ -183,9 +197,50 @@ class HotPathProver:
         if self._deep_template is None:
             L = self.layout
             taps = L.taps()
-            self._deep_template = compile_template(deep_expr_symbolic(taps, self.ce, self.comp_col, self.u_col, self.v_col, self.g, P), self.log_n,
-                                                   self.opt.log_blowup, 1, len(taps) + self.ce, 1)
+            if self.value_col is None:
+                expr = deep_expr_symbolic(taps, self.ce, self.comp_col, self.u_col, self.v_col, self.g, P)
+            else:
+                expr = deep_expr_filtered(taps, self.ce, self.comp_col, self.u_col, self.v_col, self.g, P, self.filter_cols, self.value_col)
+            self._deep_template = compile_template(expr, self.log_n, self.opt.log_blowup, 1, len(taps) + self.ce, 1)
         return self._deep_template
+
+    def deep_template_direct(self):
+        """the per-row form of the same quotient (every pole a shifted read of u): what the self-check compares against"""
+        if self.value_col is None:
+            return self.deep_template()
+        if self._deep_template_direct is None:
+            taps = self.layout.taps()
+            self._deep_template_direct = compile_template(deep_expr_symbolic(taps, self.ce, self.comp_col, self.u_col, self.v_col, self.g, P),
+                                                          self.log_n, self.opt.log_blowup, 1, len(taps) + self.ce, 1)
+        return self._deep_template_direct
+
+    def _pole_sum_on_coset(self, weights: dict, z: int, out: torch.Tensor) -> None:
+        """out[i] = sum_off weights[off] / (x_i - z g^off) on the n points x_i = 3 g^i (out: a [n, 4] view, any stride).
+        Every x_i has x_i^n = K = 3^n and every pole zeta = z g^off has zeta^n = z^n, so
+            1 / (x - zeta) = C sum_k x^k zeta^(n-1-k),  C = 1 / (K - z^n)
+        and, with B[m] = sum_off weights[off] g^(-off m) (the unnormalised inverse transform of the sparse weight vector),
+            sum = (C z^n / x_i) * sum_m D[m] g^(i m),   D[m] = B[m] (3/z)^m for m >= 1,   D[0] = B[0] K / z^n
+        (the k = n - 1 term wraps around to m = 0 with x^n = K in place of z^n).  Two size-n transforms (ss_ntt_shard stages 1
+        and 2 with the geometric scalings folded into their last / first pass) and a 32-byte fix of D[0] in between."""
+        from .parallel import DeviceShardOps
+
+        n, log_n, c = self.n, self.log_n, self.ctx
+        ops = DeviceShardOps(c)
+        inv3 = pow(3, -1, P)
+        K, zn = pow(3, n, P), pow(z, n, P)
+        c1 = pow((K - zn) % P, -1, P) * zn % P * inv3 % P                  # C z^n / 3;  1 / x_i = g^-i / 3
+        acc: dict[int, int] = {}
+        for off, w in weights.items():
+            acc[off % n] = (acc.get(off % n, 0) + w) % P
+        idx = torch.tensor(sorted(acc), dtype=torch.int64, device=self.device)
+        vals = torch.from_numpy(np.stack([_mont(acc[o]) for o in sorted(acc)]).view(np.int64)).to(self.device)
+        buf = torch.zeros((n, 4), dtype=torch.int64, device=self.device)
+        buf[idx] = vals
+        ops.ntt_shard(buf, log_n, 1, 0, c1, 3 * pow(z, -1, P) % P, None, buf)            # D[m] at position brev(m)
+        d0 = c1 * K % P * pow(zn, -1, P) % P * (sum(acc.values()) % P) % P
+        buf[0] = torch.from_numpy(_mont(d0).view(np.int64)).to(self.device)
+        ops.ntt_shard(buf, log_n, 2, 0, None, None, pow(self.g, -1, P), buf)             # natural order, times g^-i
+        out.copy_(buf)
 
     def prepare(self):
         """everything that depends only on (layout, trace length, options): call once, ahead of the proofs."""
@@ -273,7 +328,7 @@ class HotPathProver:
         self.mark("start")
         # one matrix for every committed column: trace | composition (ce) | w | u | v  (see __init__)
         S = N + opt.col_pad_rows                         # column stride of the working matrix
-        all_lde = torch.empty((C + self.ce + 3, S, 4), dtype=torch.int64, device=dev)[:, :N]
+        all_lde = torch.empty((self.n_work_cols, S, 4), dtype=torch.int64, device=dev)[:, :N]
         lde = all_lde[:C]
 
         def lde_cols(src: Matrix, first_col: int):
@@ -384,6 +439,20 @@ class HotPathProver:
         inv_x_minus_c(all_lde[self.v_col], _mont(zc), c, log_row_step=b)
         deep_prog = self.deep_template().patch([alpha], res.ood_trace + res.ood_composition, [0])
         del comp_coeffs, comp_evals, work
+        if self.value_col is not None:
+            # the long pole sums of the quotient as columns on the sub-coset rows (deep_expr_filtered): V, then W_c per heavy column
+            step = 1 << b
+            v_w: dict[int, int] = {}
+            col_w: dict[int, dict] = {col: {} for col in self.filter_cols}
+            a_k = 1
+            for (col, off), y in zip(taps, res.ood_trace):
+                v_w[off] = (v_w.get(off, 0) + a_k * y) % P
+                if col in col_w:
+                    col_w[col][off] = (col_w[col].get(off, 0) + a_k) % P
+                a_k = a_k * alpha % P
+            self._pole_sum_on_coset(v_w, z, all_lde[self.value_col, ::step])
+            for col, fcol in self.filter_cols.items():
+                self._pole_sum_on_coset(col_w[col], z, all_lde[fcol, ::step])
         # The quotient has degree < n - 1, so its n values on the sub-coset 3<w_n> — the LDE rows that are multiples of
         # the blowup — determine it: evaluate only those (1/blowup of the work), then extend like any other column
         # (coset iNTT of size n, zero padding, coset NTT of size N).  Same polynomial, hence the same N evaluations.
@@ -399,7 +468,8 @@ class HotPathProver:
             # test hook: the extended quotient equals the row-by-row evaluation on the whole LDE coset
             inv_x_minus_c(all_lde[self.u_col], _mont(z), c)
             inv_x_minus_c(all_lde[self.v_col], _mont(zc), c)
-            res.deep_matches_full_evaluation = bool(torch.equal(deep, evaluate(deep_prog, Matrix(all_lde, c), b)))
+            direct = self.deep_template_direct().patch([alpha], res.ood_trace + res.ood_composition, [0])
+            res.deep_matches_full_evaluation = bool(torch.equal(deep, evaluate(direct, Matrix(all_lde, c), b)))
         # 13: FRI layers.  Conventions pinned by the reference's proof artefacts (sandstorm_b200/verify.py): a layer commits, in
         #     bit-reversed row order, rows of the `fold` evaluations that fold together (ORDER_BITREV_RC on the evaluation
         #     buffer viewed with col_stride = rows: no data movement); the fold has no 1/fold factor; the remainder is sent as

@@ -175,3 +175,28 @@ def test_ood_values_do_not_depend_on_how_they_are_computed(ss, oracle):
     for k, (col, off) in enumerate(L.taps()):
         if k % 7 == 0:
             assert got[1][1][k] == sum(v * pow(z * pow(g, off, P) % P, e, P) for e, v in enumerate(coeffs[col])) % P
+
+
+@pytest.mark.parametrize("layout,log_n", [("recursive", 11), ("starknet", 16)])
+def test_deep_quotient_does_not_depend_on_how_its_pole_sums_are_computed(ss, oracle, layout, log_n):
+    """DEEP quotient with every pole a shifted read of u (deep_filter_min_taps=0) == with V and the tap-heavy columns' W_c taken from
+    two transforms each (default) == with EVERY column's W_c from transforms (min_taps=1): same FRI roots and remainder; and the
+    extended quotient equals the per-row form on every LDE row (self_check)."""
+    import torch
+
+    from sandstorm_b200.prover import HotPathProver, ProofOptions
+
+    rng = np.random.default_rng(9)
+    got = {}
+    for min_taps in (0, 40, 1):
+        hp = HotPathProver(layout, log_n, ProofOptions(num_queries=4, deep_filter_min_taps=min_taps))
+        L = hp.layout
+        if not got:
+            base = oracle.random_felts(rng, L.num_base_columns, 1 << log_n)
+            ext = oracle.random_felts(rng, L.num_extension_columns, 1 << log_n)
+        assert (hp.value_col is None) == (min_taps == 0)
+        res = hp.prove(ss.Matrix.from_numpy(base), ss.Matrix.from_numpy(ext), queries=False, self_check=True)
+        torch.cuda.synchronize()
+        assert res.deep_matches_full_evaluation is True
+        got[min_taps] = (res.fri_roots, res.remainder.tobytes())
+    assert got[0] == got[40] == got[1]

@@ -25,7 +25,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from sandstorm_b200.air import compile_program, compile_template  # noqa: E402
-from sandstorm_b200.air.deep import deep_expr_shifted, deep_terms  # noqa: E402
+from sandstorm_b200.air.deep import DEEP_FILTER_MIN_TAPS, deep_expr_filtered, deep_expr_shifted, deep_filter_columns, deep_terms  # noqa: E402
 from sandstorm_b200.air.expr import P  # noqa: E402
 from sandstorm_b200.air.layouts import load_layout  # noqa: E402
 from sandstorm_b200.air.program import structure_hash  # noqa: E402
@@ -118,6 +118,16 @@ def programs():
         tt, ct = deep_terms(L.taps(), [rnd.randrange(P) for _ in L.taps()], [rnd.randrange(P) for _ in range(ce)], C, rnd.randrange(P), P)
         deep = compile_program(deep_expr_shifted(tt, ct, C + ce + 1, C + ce + 2, g, P), log_n, 1, with_tables=False)
         out.append((f"{layout}_deep", deep.blob, 4))
+        # the single-GPU prover's form: long pole sums read from precomputed columns (HotPathProver.__init__ column map)
+        taps = L.taps()
+        heavy = deep_filter_columns(taps, DEEP_FILTER_MIN_TAPS)
+        if heavy or len({off for _, off in taps}) >= DEEP_FILTER_MIN_TAPS:
+            value_col = C + ce + 3
+            fcols = {col: value_col + 1 + j for j, col in enumerate(heavy)}
+            t = compile_template(deep_expr_filtered(taps, ce, C, C + ce + 1, C + ce + 2, g, P, fcols, value_col), log_n, 1, 1, len(taps) + ce, 1,
+                                 with_tables=False)
+            deepf = t.patch([rnd.randrange(P)], [rnd.randrange(P) for _ in range(len(taps) + ce)], [0])
+            out.append((f"{layout}_deepf", deepf.blob, 4))
     return out
 
 
