@@ -73,7 +73,7 @@ class ProofOptions:
     deep_filter_min_taps: int = DEEP_FILTER_MIN_TAPS   # DEEP quotient: a column with at least this many mask offsets gets its sum of
                                                  # poles W_c(x) = sum_t a_t / (x - z g^off_t) — and the layout its V(x) when it has that many
                                                  # distinct offsets — from two size-n transforms instead of one multiply-add per pole per row
-                                                 # (air/deep.py deep_expr_filtered; same values; world = 1 only; 0 disables)
+                                                 # (air/deep.py deep_expr_filtered; same values; 0 disables)
     ood_transform_min_taps: int = 32             # a column with at least this many mask offsets gets its out-of-domain values from ONE
                                                  # transform onto the coset z<g> (ss_coset_eval) instead of one n-term sum per offset;
                                                  # same values either way (0 disables)
@@ -145,7 +145,7 @@ class HotPathProver:
         self.value_col, self.filter_cols = None, {}
         taps = self.layout.taps()
         mt = self.opt.deep_filter_min_taps
-        if world == 1 and mt and log_n >= 1 and (deep_filter_columns(taps, mt) or len({off for _, off in taps}) >= mt):
+        if mt and log_n >= 1 and (deep_filter_columns(taps, mt) or len({off for _, off in taps}) >= mt):
             self.value_col = self.n_work_cols
             self.filter_cols = {col: self.value_col + 1 + j for j, col in enumerate(deep_filter_columns(taps, mt))}
             self.n_work_cols += 1 + len(self.filter_cols)
@@ -214,33 +214,36 @@ class HotPathProver:
                                                           self.log_n, self.opt.log_blowup, 1, len(taps) + self.ce, 1)
         return self._deep_template_direct
 
-    def _pole_sum_on_coset(self, weights: dict, z: int, out: torch.Tensor) -> None:
+    def _pole_sum_on_coset(self, weights: dict, z: int, out: torch.Tensor, st=None) -> None:
         """out[i] = sum_off weights[off] / (x_i - z g^off) on the n points x_i = 3 g^i (out: a [n, 4] view, any stride).
-        Every x_i has x_i^n = K = 3^n and every pole zeta = z g^off has zeta^n = z^n, so
-            1 / (x - zeta) = C sum_k x^k zeta^(n-1-k),  C = 1 / (K - z^n)
-        and, with B[m] = sum_off weights[off] g^(-off m) (the unnormalised inverse transform of the sparse weight vector),
-            sum = (C z^n / x_i) * sum_m D[m] g^(i m),   D[m] = B[m] (3/z)^m for m >= 1,   D[0] = B[0] K / z^n
-        (the k = n - 1 term wraps around to m = 0 with x^n = K in place of z^n).  Two size-n transforms (ss_ntt_shard stages 1
-        and 2 with the geometric scalings folded into their last / first pass) and a 32-byte fix of D[0] in between."""
+        Every x_i has x_i^n = K = 3^n and every pole zeta = z g^off has zeta^n = z^n, so on the coset
+            1 / (x - zeta) = C sum_{k<n} x^k zeta^(n-1-k),   C = 1 / (K - z^n),   zeta^(n-1-k) = z^(n-1-k) g^-off g^(-off k)
+        and the sum is the polynomial  C z^(n-1) sum_k (3/z)^k B[k] g^(i k)  with  B[k] = sum_off (weights[off] g^-off) g^(-off k):
+        the unnormalised inverse transform of a sparse vector, a geometric scaling and a forward transform — the local LDE
+        (ss_ntt_shard stages 1 + 2 fused) with c0 = C z^(n-1), h0 = 3/z and no expansion, whatever the number of poles.
+        st: the sharded transforms of this rank (world > 1): the same pair, split over the ranks (out then receives the owned pieces)."""
         from .parallel import DeviceShardOps
 
-        n, log_n, c = self.n, self.log_n, self.ctx
-        ops = DeviceShardOps(c)
-        inv3 = pow(3, -1, P)
+        n, log_n, g = self.n, self.log_n, self.g
         K, zn = pow(3, n, P), pow(z, n, P)
-        c1 = pow((K - zn) % P, -1, P) * zn % P * inv3 % P                  # C z^n / 3;  1 / x_i = g^-i / 3
+        c0 = pow((K - zn) % P, -1, P) * pow(z, n - 1, P) % P
+        h0 = 3 * pow(z, -1, P) % P
         acc: dict[int, int] = {}
         for off, w in weights.items():
-            acc[off % n] = (acc.get(off % n, 0) + w) % P
+            acc[off % n] = (acc.get(off % n, 0) + w * pow(g, -off, P)) % P
         idx = torch.tensor(sorted(acc), dtype=torch.int64, device=self.device)
         vals = torch.from_numpy(np.stack([_mont(acc[o]) for o in sorted(acc)]).view(np.int64)).to(self.device)
         buf = torch.zeros((n, 4), dtype=torch.int64, device=self.device)
         buf[idx] = vals
-        ops.ntt_shard(buf, log_n, 1, 0, c1, 3 * pow(z, -1, P) % P, None, buf)            # D[m] at position brev(m)
-        d0 = c1 * K % P * pow(zn, -1, P) % P * (sum(acc.values()) % P) % P
-        buf[0] = torch.from_numpy(_mont(d0).view(np.int64)).to(self.device)
-        ops.ntt_shard(buf, log_n, 2, 0, None, None, pow(self.g, -1, P), buf)             # natural order, times g^-i
-        out.copy_(buf)
+        if st is None:
+            res = torch.empty((n, 4), dtype=torch.int64, device=self.device)
+            DeviceShardOps(self.ctx).ntt_shard(buf, log_n, 3, 0, c0, h0, None, res)
+        else:
+            W, r = self.world, self.rank
+            share = st.to_coefficients(buf, log_n, c0 * pow(h0, r, P) % P, pow(h0, W, P))
+            st.from_coefficients(share, log_n - (W.bit_length() - 1), 0, buf)
+            res = buf
+        out.copy_(res)
 
     def prepare(self):
         """everything that depends only on (layout, trace length, options): call once, ahead of the proofs."""
@@ -761,7 +764,7 @@ class HotPathProver:
 
         self.mark("start")
         S = N + opt.col_pad_rows
-        all_lde = torch.empty((C + self.ce + 3, S, 4), dtype=torch.int64, device=dev)[:, :N]
+        all_lde = torch.empty((self.n_work_cols, S, 4), dtype=torch.int64, device=dev)[:, :N]
         lde = all_lde[:C]
 
         def lde_cols(src: Matrix, first_col: int):
@@ -909,6 +912,19 @@ class HotPathProver:
                 continue
             for lo, cnt in PN:
                 inv_x_minus_c(all_lde[col], _mont(point), c, log_row_step=b, rows=((lo + lo_t) >> b, min(n, (cnt + hi_t - lo_t + (1 << b) - 1) >> b)))
+        if self.value_col is not None:
+            # the long pole sums as columns on the sub-coset rows, from sharded transform pairs (see _pole_sum_on_coset)
+            v_w: dict[int, int] = {}
+            col_w: dict[int, dict] = {col: {} for col in self.filter_cols}
+            a_k = 1
+            for (col, off), y in zip(taps, res.ood_trace):
+                v_w[off] = (v_w.get(off, 0) + a_k * y) % P
+                if col in col_w:
+                    col_w[col][off] = (col_w[col].get(off, 0) + a_k) % P
+                a_k = a_k * alpha % P
+            self._pole_sum_on_coset(v_w, z, all_lde[self.value_col, ::1 << b], st)
+            for col, fcol in self.filter_cols.items():
+                self._pole_sum_on_coset(col_w[col], z, all_lde[fcol, ::1 << b], st)
         deep = torch.empty((N, 4), dtype=torch.int64, device=dev)
         quotient = torch.empty((n, 4), dtype=torch.int64, device=dev)
         self.mark("deep_setup")
