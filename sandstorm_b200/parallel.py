@@ -268,13 +268,17 @@ class ShardedTransforms:
         self.ops.dft(src, r * s, m, send, 0, s, s, self.log_w, True, log_n, r * s)
         _all_to_all(recv.view(W, s, 4), send.view(W, s, 4), W)
 
-    def lde_finish(self, log_n: int, log_blowup: int, dst: torch.Tensor, src_on_coset: bool = False, slot: int = 0) -> None:
-        """second half: the local LDE, the second all-to-all and the size-W transform into the owned pieces of dst."""
+    def lde_finish(self, log_n: int, log_blowup: int, dst: torch.Tensor, src_on_coset: bool = False, slot: int = 0, scale=None) -> None:
+        """second half: the local LDE, the second all-to-all and the size-W transform into the owned pieces of dst.
+        scale = (c, h): coefficient k of the UNNORMALISED inverse transform is multiplied by c * h^k instead of the LDE's
+        3^k / n (a transform pair onto another coset, e.g. the pole sums of the DEEP quotient)."""
         W, r = self.world, self.rank
         n = 1 << log_n
         m = n // W
         ninv = pow(n, -1, P252)
         c0, h0 = (ninv, 1) if src_on_coset else (ninv * pow(GEN, r, P252) % P252, pow(GEN, W, P252))
+        if scale is not None:
+            c0, h0 = scale[0] * pow(scale[1], r, P252) % P252, pow(scale[1], W, P252)
         recv = self._tmp(f"recv{slot}", m)
         mN = m << log_blowup
         sN = mN // W

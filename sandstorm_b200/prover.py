@@ -214,36 +214,62 @@ class HotPathProver:
                                                           self.log_n, self.opt.log_blowup, 1, len(taps) + self.ce, 1)
         return self._deep_template_direct
 
-    def _pole_sum_on_coset(self, weights: dict, z: int, out: torch.Tensor, st=None) -> None:
-        """out[i] = sum_off weights[off] / (x_i - z g^off) on the n points x_i = 3 g^i (out: a [n, 4] view, any stride).
+    def _pole_sums_on_coset(self, jobs, z: int) -> None:
+        """jobs: [(weights {offset: w}, out)];  out[i] = sum_off weights[off] / (x_i - z g^off) on the n points x_i = 3 g^i
+        (out: a [n, 4] view, any stride; with world > 1 only the owned pieces are written).
         Every x_i has x_i^n = K = 3^n and every pole zeta = z g^off has zeta^n = z^n, so on the coset
             1 / (x - zeta) = C sum_{k<n} x^k zeta^(n-1-k),   C = 1 / (K - z^n),   zeta^(n-1-k) = z^(n-1-k) g^-off g^(-off k)
         and the sum is the polynomial  C z^(n-1) sum_k (3/z)^k B[k] g^(i k)  with  B[k] = sum_off (weights[off] g^-off) g^(-off k):
         the unnormalised inverse transform of a sparse vector, a geometric scaling and a forward transform — the local LDE
         (ss_ntt_shard stages 1 + 2 fused) with c0 = C z^(n-1), h0 = 3/z and no expansion, whatever the number of poles.
-        st: the sharded transforms of this rank (world > 1): the same pair, split over the ranks (out then receives the owned pieces)."""
-        from .parallel import DeviceShardOps
+        world > 1: the same pair split over the ranks and software-pipelined over the jobs like the LDE columns."""
+        from .parallel import DeviceShardOps, pieces
 
-        n, log_n, g = self.n, self.log_n, self.g
+        n, log_n, g, dev = self.n, self.log_n, self.g, self.device
         K, zn = pow(3, n, P), pow(z, n, P)
         c0 = pow((K - zn) % P, -1, P) * pow(z, n - 1, P) % P
         h0 = 3 * pow(z, -1, P) % P
-        acc: dict[int, int] = {}
-        for off, w in weights.items():
-            acc[off % n] = (acc.get(off % n, 0) + w * pow(g, -off, P)) % P
-        idx = torch.tensor(sorted(acc), dtype=torch.int64, device=self.device)
-        vals = torch.from_numpy(np.stack([_mont(acc[o]) for o in sorted(acc)]).view(np.int64)).to(self.device)
-        buf = torch.zeros((n, 4), dtype=torch.int64, device=self.device)
-        buf[idx] = vals
-        if st is None:
-            res = torch.empty((n, 4), dtype=torch.int64, device=self.device)
-            DeviceShardOps(self.ctx).ntt_shard(buf, log_n, 3, 0, c0, h0, None, res)
-        else:
-            W, r = self.world, self.rank
-            share = st.to_coefficients(buf, log_n, c0 * pow(h0, r, P) % P, pow(h0, W, P))
-            st.from_coefficients(share, log_n - (W.bit_length() - 1), 0, buf)
-            res = buf
-        out.copy_(res)
+        W, r = self.world, self.rank
+        mine = pieces(log_n, r, W) if W > 1 else [(0, n)]
+        srcs = []
+        for weights, _ in jobs:
+            acc: dict[int, int] = {}
+            for off, w in weights.items():
+                acc[off % n] = (acc.get(off % n, 0) + w * pow(g, -off, P)) % P
+            idx = torch.tensor(sorted(acc), dtype=torch.int64, device=dev)
+            vals = torch.from_numpy(np.stack([_mont(acc[o]) for o in sorted(acc)]).view(np.int64)).to(dev)
+            buf = torch.empty((n, 4), dtype=torch.int64, device=dev)
+            for lo, cnt in mine:
+                buf[lo:lo + cnt].zero_()
+            buf[idx] = vals                                  # (entries outside the owned pieces are never read)
+            srcs.append(buf)
+        if W == 1:
+            res = torch.empty((n, 4), dtype=torch.int64, device=dev)
+            for buf, (_, out) in zip(srcs, jobs):
+                DeviceShardOps(self.ctx).ntt_shard(buf, log_n, 3, 0, c0, h0, None, res)
+                out.copy_(res)
+            return
+        main = torch.cuda.current_stream()
+        pipes = self._lde_pipes(dev, W, r)
+        for stream, _ in pipes:
+            stream.wait_stream(main)
+
+        def begin(j):
+            stream, stx = pipes[j & 1]
+            with torch.cuda.stream(stream):
+                stx.lde_begin(srcs[j], log_n, slot=j & 1)
+
+        begin(0)
+        for j, (_, out) in enumerate(jobs):
+            if j + 1 < len(jobs):
+                begin(j + 1)
+            stream, stx = pipes[j & 1]
+            with torch.cuda.stream(stream):
+                stx.lde_finish(log_n, 0, srcs[j], slot=j & 1, scale=(c0, h0))      # (the source is consumed by then: reuse it)
+                for lo, cnt in mine:
+                    out[lo:lo + cnt].copy_(srcs[j][lo:lo + cnt])
+        for stream, _ in pipes:
+            main.wait_stream(stream)
 
     def prepare(self):
         """everything that depends only on (layout, trace length, options): call once, ahead of the proofs."""
@@ -453,9 +479,8 @@ class HotPathProver:
                 if col in col_w:
                     col_w[col][off] = (col_w[col].get(off, 0) + a_k) % P
                 a_k = a_k * alpha % P
-            self._pole_sum_on_coset(v_w, z, all_lde[self.value_col, ::step])
-            for col, fcol in self.filter_cols.items():
-                self._pole_sum_on_coset(col_w[col], z, all_lde[fcol, ::step])
+            self._pole_sums_on_coset([(v_w, all_lde[self.value_col, ::step])] +
+                                     [(col_w[col], all_lde[fcol, ::step]) for col, fcol in self.filter_cols.items()], z)
         # The quotient has degree < n - 1, so its n values on the sub-coset 3<w_n> — the LDE rows that are multiples of
         # the blowup — determine it: evaluate only those (1/blowup of the work), then extend like any other column
         # (coset iNTT of size n, zero padding, coset NTT of size N).  Same polynomial, hence the same N evaluations.
@@ -860,7 +885,8 @@ class HotPathProver:
         per_col = {}
         for col, _ in taps:
             per_col[col] = per_col.get(col, 0) + 1
-        heavy = {col for col, cnt in per_col.items() if opt.ood_transform_min_taps and cnt >= opt.ood_transform_min_taps}
+        # (a sharded pair costs two exchanges: it only pays for twice as many taps as on one GPU)
+        heavy = {col for col, cnt in per_col.items() if opt.ood_transform_min_taps and cnt >= 2 * opt.ood_transform_min_taps}
         if heavy:
             # tap-heavy columns: T(z g^j) for every j by one more sharded transform pair (coefficients scaled by z^k, then the
             # forward transform without expansion); the mask offsets are then read from their owners.  Same values as the sums.
@@ -922,9 +948,8 @@ class HotPathProver:
                 if col in col_w:
                     col_w[col][off] = (col_w[col].get(off, 0) + a_k) % P
                 a_k = a_k * alpha % P
-            self._pole_sum_on_coset(v_w, z, all_lde[self.value_col, ::1 << b], st)
-            for col, fcol in self.filter_cols.items():
-                self._pole_sum_on_coset(col_w[col], z, all_lde[fcol, ::1 << b], st)
+            self._pole_sums_on_coset([(v_w, all_lde[self.value_col, ::1 << b])] +
+                                     [(col_w[col], all_lde[fcol, ::1 << b]) for col, fcol in self.filter_cols.items()], z)
         deep = torch.empty((N, 4), dtype=torch.int64, device=dev)
         quotient = torch.empty((n, 4), dtype=torch.int64, device=dev)
         self.mark("deep_setup")
