@@ -222,7 +222,7 @@ class HotPathProver:
         and the sum is the polynomial  C z^(n-1) sum_k (3/z)^k B[k] g^(i k)  with  B[k] = sum_off (weights[off] g^-off) g^(-off k):
         the unnormalised inverse transform of a sparse vector, a geometric scaling and a forward transform — the local LDE
         (ss_ntt_shard stages 1 + 2 fused) with c0 = C z^(n-1), h0 = 3/z and no expansion, whatever the number of poles.
-        world > 1: the same pair split over the ranks and software-pipelined over the jobs like the LDE columns."""
+        world > 1: the same pair split over the ranks (parallel.ShardedTransforms)."""
         from .parallel import DeviceShardOps, pieces
 
         n, log_n, g, dev = self.n, self.log_n, self.g, self.device
@@ -231,45 +231,32 @@ class HotPathProver:
         h0 = 3 * pow(z, -1, P) % P
         W, r = self.world, self.rank
         mine = pieces(log_n, r, W) if W > 1 else [(0, n)]
-        srcs = []
-        for weights, _ in jobs:
+        from .parallel import ShardedTransforms
+
+        buf = torch.empty((n, 4), dtype=torch.int64, device=dev)
+        res = torch.empty((n, 4), dtype=torch.int64, device=dev) if W == 1 else None
+        if W > 1 and getattr(self, "_pole_st", None) is None:
+            # (software-pipelining these pairs over the two LDE pipes was measured SLOWER at 8 GPUs — 57 vs 30 ms for four
+            #  pairs — so they run back to back on the caller's stream)
+            self._pole_st = ShardedTransforms(r, W, DeviceShardOps(self.ctx), dev)
+        for weights, out in jobs:
             acc: dict[int, int] = {}
             for off, w in weights.items():
                 acc[off % n] = (acc.get(off % n, 0) + w * pow(g, -off, P)) % P
             idx = torch.tensor(sorted(acc), dtype=torch.int64, device=dev)
             vals = torch.from_numpy(np.stack([_mont(acc[o]) for o in sorted(acc)]).view(np.int64)).to(dev)
-            buf = torch.empty((n, 4), dtype=torch.int64, device=dev)
             for lo, cnt in mine:
                 buf[lo:lo + cnt].zero_()
             buf[idx] = vals                                  # (entries outside the owned pieces are never read)
-            srcs.append(buf)
-        if W == 1:
-            res = torch.empty((n, 4), dtype=torch.int64, device=dev)
-            for buf, (_, out) in zip(srcs, jobs):
+            if W == 1:
                 DeviceShardOps(self.ctx).ntt_shard(buf, log_n, 3, 0, c0, h0, None, res)
                 out.copy_(res)
-            return
-        main = torch.cuda.current_stream()
-        pipes = self._lde_pipes(dev, W, r)
-        for stream, _ in pipes:
-            stream.wait_stream(main)
-
-        def begin(j):
-            stream, stx = pipes[j & 1]
-            with torch.cuda.stream(stream):
-                stx.lde_begin(srcs[j], log_n, slot=j & 1)
-
-        begin(0)
-        for j, (_, out) in enumerate(jobs):
-            if j + 1 < len(jobs):
-                begin(j + 1)
-            stream, stx = pipes[j & 1]
-            with torch.cuda.stream(stream):
-                stx.lde_finish(log_n, 0, srcs[j], slot=j & 1, scale=(c0, h0))      # (the source is consumed by then: reuse it)
-                for lo, cnt in mine:
-                    out[lo:lo + cnt].copy_(srcs[j][lo:lo + cnt])
-        for stream, _ in pipes:
-            main.wait_stream(stream)
+                continue
+            st = self._pole_st
+            share = st.to_coefficients(buf, log_n, c0 * pow(h0, r, P) % P, pow(h0, W, P))
+            st.from_coefficients(share, log_n - (W.bit_length() - 1), 0, buf)
+            for lo, cnt in mine:
+                out[lo:lo + cnt].copy_(buf[lo:lo + cnt])
 
     def prepare(self):
         """everything that depends only on (layout, trace length, options): call once, ahead of the proofs."""
