@@ -129,14 +129,23 @@ __device__ __forceinline__ void stage(Fp (&x)[8], int base, int q, int q0, int L
         const unsigned int tau0 = (unsigned int)(base | (i0 << q));
         const unsigned int l0 = (tau0 >> q0) & ((1u << L) - 1u);
         const unsigned int tw_idx = (l0 & ((1u << bl) - 1u)) << (11 - bl);
+        // w^0 = 1: no multiplication.  In the round that holds the lowest transform bits the index depends on register bits only
+        // (the same for every thread of the warp), so half of the bl = 1 and a quarter of the bl = 2 butterflies really skip it.
+        const bool unit = bl == 0 || tw_idx == 0;
         if (DIT) {
-            const Fp tm = (bl == 0) ? x[i1] : fp::mul(x[i1], ldg_fp(tw_local + tw_idx));
+            Fp tm;
+            if (unit) {
+                tm = x[i1];
+                if (bl != 0) { fp::cond_sub_4p(tm); fp::cond_sub_2p(tm); }     // (a product would have come back below 2p)
+            } else {
+                tm = fp::mul(x[i1], ldg_fp(tw_local + tw_idx));
+            }
             x[i1] = fp::sub2p(x[i0], tm);
             x[i0] = fp::add_raw(x[i0], tm);
         } else {
             const Fp d = fp::sub4p(x[i0], x[i1]);
             x[i0] = fp::add_fast(x[i0], x[i1]);
-            if (bl == 0) { x[i1] = d; fp::cond_sub_4p(x[i1]); fp::cond_sub_2p(x[i1]); }
+            if (unit) { x[i1] = d; fp::cond_sub_4p(x[i1]); fp::cond_sub_2p(x[i1]); }
             else x[i1] = fp::mul(d, ldg_fp(tw_local + tw_idx));
         }
     }
