@@ -6,8 +6,10 @@
 // (contiguous tiles when b0 = 0).  DIF (Gentleman-Sande) maps natural -> bit-reversed order and walks the bit groups
 // from the top; DIT (Cooley-Tukey) maps bit-reversed -> natural and walks them from the bottom — the same split as
 // the Fp252 kernels (ntt_fp252.cuh), so ss_lde = inverse DIF, scale, zero-padded forward DIT with no permutation.
-// Twiddles w_N^e come from two cached tables (e mod 4096, e div 4096): one extra multiplication instead of an
-// N/2-entry table.  Algorithmic bytes: 2 * 8 B per element per pass.
+// Four-step form: the stages of a pass take their twiddles from ONE 4096-entry table (w_8192^k, L1-resident), and a strided
+// pass multiplies every element once by w_N^e between the passes (two cached tables: e mod 4096, e div 4096).  2^24 points =
+// 13 + 11 bits: two passes.  Algorithmic bytes: 2 * 8 B per element per pass; the kernel is bound by instruction issue, not
+// HBM.
 #include "ctx.h"
 #include "goldilocks.cuh"
 
@@ -15,19 +17,26 @@ using namespace ss;
 
 namespace {
 
-constexpr int GL_THREADS = 256;
-constexpr int GL_LOG_TILE = 12;                 // 4096 elements = 32 KB of shared memory per block
-constexpr int GL_LOG_W = 3;                     // strided passes move runs of 8 elements (64 bytes)
-constexpr int T_GL_LO = 40, T_GL_HI = 41, T_GL_PLO = 42, T_GL_PHI = 43;
+constexpr int GL_THREADS = 512;
+constexpr int GL_LOG_TILE = 13;                 // 8192 elements = 64 KB of shared memory per block
+constexpr int GL_LOG_W = 2;                     // strided passes move runs of 4 elements (one 32-byte sector)
+constexpr int T_GL_LO = 40, T_GL_HI = 41, T_GL_PLO = 42, T_GL_PHI = 43, T_GL_LOCAL = 44;
 
 struct GlPassArgs {
     uint64_t *data;                             // column 0
     unsigned long long stride;                  // elements between columns
     int log_n, b0, S, c;                        // bit group [b0, b0 + S), W = 2^c
-    const uint64_t *tw_lo, *tw_hi;              // w^e (e < 4096), w^(4096 e)
+    const uint64_t *tw_local;                   // w_(2^GL_LOG_TILE)^k, k < 2^(GL_LOG_TILE - 1): every in-tile twiddle
+    const uint64_t *tw_lo, *tw_hi;              // w_N^e (e < 4096), w_N^(4096 e): the twiddles between the passes
 };
 
-__device__ __forceinline__ uint64_t twiddle(const GlPassArgs &A, unsigned long long e) {
+// Four-step form: a pass is a plain size-2^S transform of the tile's index bits (twiddles from ONE small table, no
+// multiplication to build them) and, for a strided pass, one multiplication per element by w_M^(lo * brev_S(l)), M = 2^(b0+S),
+// lo = the index bits below the group, l = the element's (bit-reversed) position inside the group — after the stages for DIF,
+// before them for DIT (the transposed factorisation).
+__device__ __forceinline__ uint64_t interpass(const GlPassArgs &A, unsigned int j, unsigned long long lo) {
+    const unsigned long long r = (unsigned long long)(__brev(j) >> (32 - A.S));
+    const unsigned long long e = (lo * r) << (A.log_n - A.b0 - A.S);
     uint64_t w = __ldg(A.tw_lo + (e & 4095ull));
     if (e >> 12) w = gl::mul(w, __ldg(A.tw_hi + (e >> 12)));
     return w;
@@ -36,7 +45,7 @@ __device__ __forceinline__ uint64_t twiddle(const GlPassArgs &A, unsigned long l
 template <bool DIT>
 __global__ void __launch_bounds__(GL_THREADS) gl_pass_kernel(const GlPassArgs A) {
     extern __shared__ uint64_t sm[];
-    const int S = A.S, c = A.c, b0 = A.b0, L = A.log_n;
+    const int S = A.S, c = A.c, b0 = A.b0;
     const unsigned int W = 1u << c, T = 1u << (S + c);
     uint64_t *col = A.data + (unsigned long long)blockIdx.y * A.stride;
     const unsigned long long tile = blockIdx.x;
@@ -45,34 +54,84 @@ __global__ void __launch_bounds__(GL_THREADS) gl_pass_kernel(const GlPassArgs A)
     const unsigned long long base = (hi << (b0 + S)) | lo_base;
     for (unsigned int e = threadIdx.x; e < T; e += GL_THREADS) {
         const unsigned int j = e >> c, l = e & (W - 1);
-        sm[e] = col[base | ((unsigned long long)j << b0) | l];
+        uint64_t v = col[base | ((unsigned long long)j << b0) | l];
+        if (DIT && b0 > 0) v = gl::mul(v, interpass(A, j, lo_base | l));
+        sm[e] = v;
     }
     __syncthreads();
-    for (int step = 0; step < S; ++step) {
-        const int sl = DIT ? step : S - 1 - step;            // local stage: pairs (j, j + 2^sl)
-        const unsigned int h = 1u << sl;
-        const int s = b0 + sl;                                // global bit of the stage
-        for (unsigned int q = threadIdx.x; q < T / 2; q += GL_THREADS) {
-            const unsigned int l = q & (W - 1), r = q >> c;
-            const unsigned int j = ((r >> sl) << (sl + 1)) | (r & (h - 1));
-            const unsigned long long low = ((unsigned long long)(j & (h - 1)) << b0) | lo_base | l;     // i mod 2^s
-            const uint64_t w = twiddle(A, low << (L - 1 - s));
-            const unsigned int ia = (j << c) | l, ib = ((j + h) << c) | l;
-            const uint64_t a = sm[ia], b = sm[ib];
-            if (DIT) {
-                const uint64_t t = gl::mul(b, w);
-                sm[ia] = gl::add(a, t);
-                sm[ib] = gl::sub(a, t);
-            } else {
-                sm[ia] = gl::add(a, b);
-                sm[ib] = gl::mul(gl::sub(a, b), w);
+    // two stages per round in registers (four elements per thread and round: half the shared-memory traffic and barriers of a
+    // radix-2 sweep); a last single stage when S is odd
+    int done = 0;
+    while (done < S) {
+        if (S - done >= 2) {
+            const int s0 = DIT ? done : S - 2 - done, s1 = s0 + 1;           // the lower / upper stage of the round
+            const unsigned int h0 = 1u << s0;
+            const int sh0 = GL_LOG_TILE - 1 - s0, sh1 = GL_LOG_TILE - 1 - s1;
+            for (unsigned int q = threadIdx.x; q < T / 4; q += GL_THREADS) {
+                const unsigned int l = q & (W - 1), r = q >> c;
+                const unsigned int k = r & (h0 - 1);
+                const unsigned int j = ((r >> s0) << (s0 + 2)) | k;
+                const unsigned int i0 = (j << c) | l, i1 = ((j + h0) << c) | l, i2 = ((j + 2 * h0) << c) | l, i3 = ((j + 3 * h0) << c) | l;
+                uint64_t x0 = sm[i0], x1 = sm[i1], x2 = sm[i2], x3 = sm[i3];
+                const uint64_t w1a = __ldg(A.tw_local + ((unsigned long long)k << sh1));
+                const uint64_t w1b = __ldg(A.tw_local + ((unsigned long long)(k + h0) << sh1));
+                if (DIT) {
+                    if (s0 != 0) {
+                        const uint64_t w0 = __ldg(A.tw_local + ((unsigned long long)k << sh0));
+                        x1 = gl::mul(x1, w0);
+                        x3 = gl::mul(x3, w0);
+                    }
+                    const uint64_t a = gl::add(x0, x1), bb = gl::sub(x0, x1), cc = gl::add(x2, x3), d = gl::sub(x2, x3);
+                    const uint64_t tc = gl::mul(cc, w1a), td = gl::mul(d, w1b);
+                    x0 = gl::add(a, tc); x2 = gl::sub(a, tc);
+                    x1 = gl::add(bb, td); x3 = gl::sub(bb, td);
+                } else {
+                    const uint64_t a = gl::add(x0, x2), cc = gl::mul(gl::sub(x0, x2), w1a);
+                    const uint64_t bb = gl::add(x1, x3), d = gl::mul(gl::sub(x1, x3), w1b);
+                    x0 = gl::add(a, bb); x1 = gl::sub(a, bb);
+                    x2 = gl::add(cc, d); x3 = gl::sub(cc, d);
+                    if (s0 != 0) {
+                        const uint64_t w0 = __ldg(A.tw_local + ((unsigned long long)k << sh0));
+                        x1 = gl::mul(x1, w0);
+                        x3 = gl::mul(x3, w0);
+                    }
+                }
+                sm[i0] = x0; sm[i1] = x1; sm[i2] = x2; sm[i3] = x3;
             }
+            done += 2;
+        } else {
+            const int sl = DIT ? done : 0;                                   // the one stage left: the top one (DIT) or stage 0 (DIF)
+            const unsigned int h = 1u << sl;
+            for (unsigned int q = threadIdx.x; q < T / 2; q += GL_THREADS) {
+                const unsigned int l = q & (W - 1), r = q >> c;
+                const unsigned int k = r & (h - 1);
+                const unsigned int j = ((r >> sl) << (sl + 1)) | k;
+                const unsigned int ia = (j << c) | l, ib = ((j + h) << c) | l;
+                const uint64_t a = sm[ia], bv = sm[ib];
+                if (sl == 0) {
+                    sm[ia] = gl::add(a, bv);
+                    sm[ib] = gl::sub(a, bv);
+                } else {
+                    const uint64_t w = __ldg(A.tw_local + ((unsigned long long)k << (GL_LOG_TILE - 1 - sl)));
+                    if (DIT) {
+                        const uint64_t t = gl::mul(bv, w);
+                        sm[ia] = gl::add(a, t);
+                        sm[ib] = gl::sub(a, t);
+                    } else {
+                        sm[ia] = gl::add(a, bv);
+                        sm[ib] = gl::mul(gl::sub(a, bv), w);
+                    }
+                }
+            }
+            done += 1;
         }
         __syncthreads();
     }
     for (unsigned int e = threadIdx.x; e < T; e += GL_THREADS) {
         const unsigned int j = e >> c, l = e & (W - 1);
-        col[base | ((unsigned long long)j << b0) | l] = sm[e];
+        uint64_t v = sm[e];
+        if (!DIT && b0 > 0) v = gl::mul(v, interpass(A, j, lo_base | l));
+        col[base | ((unsigned long long)j << b0) | l] = v;
     }
 }
 
@@ -138,10 +197,15 @@ ss_status run_passes(ss_ctx *ctx, uint64_t *data, unsigned long long stride, int
     if (log_n == 0) return SS_OK;
     uint64_t w = gl::root_of_unity(log_n);
     if (inverse) w = gl::inv(w);
-    const uint64_t *lo, *hi;
-    ss_status rc = power_tables(ctx, T_GL_LO, T_GL_HI, log_n, inverse ? 1 : 0, w, (size_t)1 << (log_n - 1), &lo, &hi);
+    const uint64_t *lo, *hi, *local, *unused;
+    ss_status rc = power_tables(ctx, T_GL_LO, T_GL_HI, log_n, inverse ? 1 : 0, w, (size_t)1 << log_n, &lo, &hi);
     if (rc) return rc;
-    // bit groups, lowest first: one contiguous group of up to 12 bits at b0 = 0, strided groups of up to 9 bits above it
+    uint64_t wt = gl::root_of_unity(GL_LOG_TILE);
+    if (inverse) wt = gl::inv(wt);
+    // (keyed by the tile size: one table of 2^(GL_LOG_TILE-1) in-tile twiddles per direction, shared by every transform length)
+    if ((rc = power_tables(ctx, T_GL_LOCAL, T_GL_LOCAL + 100, GL_LOG_TILE, inverse ? 1 : 0, wt, (size_t)1 << (GL_LOG_TILE - 1), &local, &unused))) return rc;
+    // bit groups, lowest first: one contiguous group of up to GL_LOG_TILE bits at b0 = 0, strided groups of up to
+    // GL_LOG_TILE - GL_LOG_W bits above it (2^24 = 13 + 11: two passes)
     struct Group { int b0, S, c; };
     std::vector<Group> groups;
     const int first = log_n < GL_LOG_TILE ? log_n : GL_LOG_TILE;
@@ -152,7 +216,8 @@ ss_status run_passes(ss_ctx *ctx, uint64_t *data, unsigned long long stride, int
         int b = first;
         for (int g = 0; g < n_g; ++g) {
             const int S = rest / n_g + (g < rest % n_g ? 1 : 0);
-            groups.push_back({b, S, GL_LOG_W});
+            const int c = GL_LOG_TILE - S < b ? GL_LOG_TILE - S : b;      // fill the tile: short groups move longer runs
+            groups.push_back({b, S, c});
             b += S;
         }
     }
@@ -164,7 +229,7 @@ ss_status run_passes(ss_ctx *ctx, uint64_t *data, unsigned long long stride, int
     }
     for (size_t k = 0; k < groups.size(); ++k) {
         const Group g = dit ? groups[k] : groups[groups.size() - 1 - k];       // DIT: low bits first; DIF: high bits first
-        GlPassArgs A{data, stride, log_n, g.b0, g.S, g.c, lo, hi};
+        GlPassArgs A{data, stride, log_n, g.b0, g.S, g.c, local, lo, hi};
         const dim3 grid((unsigned)(1ull << (log_n - g.S - g.c)), (unsigned)n_cols, 1);
         const size_t smem = (size_t)8 << (g.S + g.c);
         if (dit) gl_pass_kernel<true><<<grid, GL_THREADS, smem, st>>>(A);

@@ -77,7 +77,7 @@ def _brev_perm(log_n):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("log_n", [0, 1, 2, 5, 11, 12, 13, 16, 21])
+@pytest.mark.parametrize("log_n", [0, 1, 2, 5, 11, 12, 13, 14, 16, 21])
 def test_gpu_ntt_matches_oracle(ss, oracle, log_n):
     import torch
 
@@ -111,6 +111,23 @@ def test_gpu_lde_matches_oracle(ss, oracle, log_n, log_blowup):
     a = rng.integers(0, P, size=(2, 1 << log_n), dtype=np.uint64)
     got = glk.lde(torch.from_numpy(a.view(np.int64)).cuda(), log_blowup).cpu().numpy().view(np.uint64)
     assert np.array_equal(got, oracle.gl_lde(a, log_blowup))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("log_n", [24, 25])
+def test_gpu_ntt_matches_oracle_two_and_three_passes(ss, oracle, log_n):
+    """2^24 = 13 + 11 bits (two passes), 2^25 = 13 + 6 + 6 (three): coset NTT and its inverse against the oracle, one column."""
+    import torch
+
+    from sandstorm_b200 import goldilocks as glk
+
+    a = np.random.default_rng(log_n).integers(0, P, size=(1, 1 << log_n), dtype=np.uint64)
+    want = oracle.gl_ntt(a, False, True)
+    t = torch.from_numpy(a.view(np.int64)).cuda()
+    glk.ntt_(t, coset=True)
+    assert np.array_equal(t.cpu().numpy().view(np.uint64), want)
+    glk.ntt_(t, inverse=True, coset=True)
+    assert np.array_equal(t.cpu().numpy().view(np.uint64), a)
 
 
 @pytest.mark.gpu

@@ -1,36 +1,18 @@
-#!/usr/bin/env python3
-"""Goldilocks NTT microbench (BASELINE config 5 shape for the single-limb field): batched forward coset NTT,
-field-ops/s and achieved HBM GB/s (algorithmic bytes = 2 * 8 B per element per pass).  Usage: bench_goldilocks.py [log_n ...]"""
-import json
-import os
-import sys
-
-import torch
-
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import sandstorm_b200 as ss  # noqa: E402
-from sandstorm_b200 import goldilocks as glk  # noqa: E402
-
-for log_n in [int(v) for v in sys.argv[1:]] or [16, 20, 24, 26]:
-    n_cols = max(1, min(64, (1 << 29) >> (log_n + 3)))          # ~512 MiB per batch
-    g = torch.Generator(device="cuda").manual_seed(log_n)
-    a = torch.randint(0, 2**62, (n_cols, 1 << log_n), dtype=torch.int64, device="cuda", generator=g)
-    for _ in range(2):
-        glk.ntt_(a, coset=False, out_order=ss.ORDER_BITREV)
+import torch, time, sys
+sys.path.insert(0, '/root/repo')
+import sandstorm_b200 as ss
+from sandstorm_b200 import goldilocks as glk
+for log_n, cols in ((20, 64), (24, 8), (26, 4)):
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a = torch.randint(0, 2**62, (cols, 1 << log_n), dtype=torch.int64, device="cuda", generator=g)
+    for _ in range(2): glk.ntt_(a); glk.ntt_(a, inverse=True)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 5
     e0.record()
-    for _ in range(reps):
-        glk.ntt_(a, coset=False, out_order=ss.ORDER_BITREV)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
-    passes = 1 if log_n <= 12 else 1 + -(-(log_n - 12) // 9)
-    ops = 1.5 * (1 << log_n) * log_n * n_cols
-    rec = {"field": "goldilocks", "log_n": log_n, "n_cols": n_cols, "ms": round(ms, 4), "field_ops_per_s": ops / (ms * 1e-3), "passes": passes,
-           "algo_GBps": n_cols * (1 << log_n) * 16 * passes / (ms * 1e-3) / 1e9}
-    print(json.dumps(rec), flush=True)
-    os.makedirs("gpurun_out", exist_ok=True)
-    with open("gpurun_out/bench_goldilocks.jsonl", "a") as f:
-        f.write(json.dumps(rec) + "\n")
+    reps = 5
+    for _ in range(reps): glk.ntt_(a, in_order=ss.ORDER_NATURAL, out_order=ss.ORDER_BITREV); glk.ntt_(a, inverse=True, in_order=ss.ORDER_BITREV, out_order=ss.ORDER_NATURAL)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / (2 * reps)
+    n = 1 << log_n
+    ops = cols * 1.5 * n * log_n
+    print(f"2^{log_n} x {cols}: {ms:.3f} ms per transform batch, {ops / ms / 1e6:.1f} Gfield-ops/s, {cols * n * 16 / ms / 1e6:.1f} GB/s algorithmic (read once + write once)")
