@@ -316,6 +316,63 @@ def ntt_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def goldilocks_arm(args):
+    """BASELINE configs[3]: the single-limb NTT path on the shape of a recursive-layout trace (10 columns) over Goldilocks:
+    per-column LDE (interpolate on <w_n>, evaluate on 7<w_2n>), columns split over the ranks (they shard embarrassingly:
+    no exchange).  Default 2^24 Cairo steps = 2^28 rows; reduced until the columns of a rank fit its memory."""
+    import torch
+
+    from sandstorm_b200 import goldilocks as glk
+
+    rank, local, world = init_dist()
+    peak, peak_src = peaks()
+    n_cols_total = 10
+    log_n = (args.log_steps or 24) + CYCLE_HEIGHT_LOG
+    mine = [k for k in range(n_cols_total) if k % world == rank]
+    free_b, _ = torch.cuda.mem_get_info()
+    while len(mine) * 8 * 4 * (1 << log_n) > 0.8 * free_b and log_n > 16:      # trace + LDE + coefficient scratch
+        log_n -= 1
+    g = torch.Generator(device="cuda").manual_seed(3 + rank)
+    trace = torch.randint(0, 2**62, (len(mine), 1 << log_n), dtype=torch.int64, device="cuda", generator=g)
+
+    def step():
+        return glk.lde(trace, 1)
+
+    for _ in range(args.warmup):
+        step()
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    with ClockSampler(local) as clk:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            out = step()
+        e1.record()
+        torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms = float(t[0])
+    if rank != 0:
+        return
+    n = 1 << log_n
+    ops = n_cols_total * (1.5 * n * log_n + 1.5 * 2 * n * (log_n + 1))          # inverse transform of n + forward transform of 2n per column
+    per_gpu_bytes = len(mine) * (n * 8 + 2 * n * 8)                              # SURVEY §8(d): n s + N s per LDE column
+    gbs = per_gpu_bytes / (ms * 1e-3) / 1e9
+    line = {"metric": "ntt_field_ops_per_s", "value": ops / (ms * 1e-3), "unit": "field-ops/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u64 (Goldilocks, stored words)", "data": "synthetic",
+            "config": {"workload": f"Goldilocks LDE (blowup 2) of {n_cols_total} columns x 2^{log_n} rows, columns split over the ranks",
+                       "requested_log_steps": args.log_steps or 24, "l2": "inputs_larger_than_L2", "columns_on_rank_0": len(mine)},
+            "clocks": clk.summary(), "gpu_launches": None,
+            "roofline": {"bound": "hbm", "kernel": "gl_pass_kernel (ss_lde, SS_FIELD_GOLDILOCKS)", "achieved": gbs, "peak": peak, "unit": "GB/s",
+                         "frac": gbs / peak, "traffic": None, "peak_source": peak_src,
+                         "note": "algorithmic bytes n*8 + N*8 per column on the busiest rank; the transform is bound by instruction issue "
+                                 "(~380 instructions per element at best, DESIGN.md §4.7), not HBM"}}
+    print(json.dumps(line), flush=True)
+
+
 def gpu_arm(args):
     import torch
 
@@ -511,7 +568,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="starknet22", choices=["starknet22", "recursive20", "ntt"])
+    ap.add_argument("--workload", default="starknet22", choices=["starknet22", "recursive20", "ntt", "goldilocks"])
     ap.add_argument("--log-steps", type=int, default=0, help="log2 of Cairo steps (default: the workload's; n = 16 * steps)")
     ap.add_argument("--cpu-log-n", type=int, default=17, help="log2 rows of the bounded CPU sample (cpu_baseline / --impl reference)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -521,6 +578,8 @@ def main():
         reference_arm(args)
     elif args.workload == "ntt":
         ntt_arm(args)
+    elif args.workload == "goldilocks":
+        goldilocks_arm(args)
     else:
         gpu_arm(args)
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
