@@ -944,11 +944,13 @@ class HotPathProver:
             evaluate(deep_prog, Matrix(all_lde, c), b, out=quotient, rows=(lo, cnt >> b), log_row_step=b)
         self.mark("deep")
         lde_one(quotient, deep, on_coset=True)
+        self.mark("deep_lde")
+        # 13: FRI.  Every rank needs the whole evaluation vector for the layers (their fold groups and leaf ranges do not follow
+        #     the block-cyclic pieces): one all-gather, timed with the FRI stage it serves
         if capi:
             c.check(c.lib.ss_dist_allgather(c.handle, ctypes.c_void_p(deep.data_ptr()), log_N, _stream_ptr()))
         else:
             self._gather_pieces(deep, log_N)
-        self.mark("deep_lde")
         del comp_evals, quotient
         # 13: FRI layers on the gathered evaluations (tree-leaf / row ranges per rank while the layers are large)
         evals, log_size, offset = deep, log_N, 3
