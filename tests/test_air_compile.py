@@ -158,6 +158,20 @@ def test_generated_kernel_registry_matches_prover_programs(name, log_n):
     deep = compile_program(deep_expr_shifted(tt, ct, C + ce + 1, C + ce + 2, pow(3, (P - 1) // n, P), P), log_n, 1, with_tables=False)
     assert registry.get(structure_hash(comp.blob), "").startswith(f"{name}_composition")
     assert registry.get(structure_hash(deep.blob), "").startswith(f"{name}_deep")
+    # the form the prover runs when the layout has long pole sums (prover.HotPathProver.__init__ decides the same way)
+    from sandstorm_b200.air.deep import DEEP_FILTER_MIN_TAPS, deep_expr_filtered, deep_filter_columns
+
+    taps = L.taps()
+    heavy = deep_filter_columns(taps, DEEP_FILTER_MIN_TAPS)
+    if heavy or len({off for _, off in taps}) >= DEEP_FILTER_MIN_TAPS:
+        value_col = C + ce + 3
+        fcols = {col: value_col + 1 + j for j, col in enumerate(heavy)}
+        t = compile_template(deep_expr_filtered(taps, ce, C, C + ce + 1, C + ce + 2, pow(3, (P - 1) // n, P), P, fcols, value_col), log_n, 1, 1,
+                             len(taps) + ce, 1, with_tables=False)
+        deepf = t.patch([rnd.randrange(P)], [rnd.randrange(P) for _ in range(len(taps) + ce)], [0])
+        assert registry.get(structure_hash(deepf.blob), "").startswith(f"{name}_deepf")
+    else:
+        assert name == "plain"
 
 
 @pytest.mark.parametrize("special_hints", [False, True])
@@ -231,3 +245,83 @@ def test_deep_template_patch_is_the_direct_compilation(name, log_n):
         ood, oc, alpha = [rnd.randrange(P) for _ in taps], [rnd.randrange(P) for _ in range(ce)], rnd.randrange(P)
         tt, ct = deep_terms(taps, ood, oc, C, alpha, P)
         assert tpl.patch([alpha], ood + oc, [0]).blob == compile_program(deep_expr_shifted(tt, ct, C + ce + 1, C + ce + 2, g, P), log_n, 1).blob
+
+
+def _pole_sum_by_transforms(weights, z, n, g):
+    """prover._pole_sums_on_coset in big ints: inverse transform of the sparse vector weights[off] g^-off, scaling by
+    C z^(n-1) (3/z)^k, forward transform.  -> [sum_off weights[off] / (3 g^i - z g^off) for i < n]."""
+    K, zn = pow(3, n, P), pow(z, n, P)
+    c0 = pow((K - zn) % P, -1, P) * pow(z, n - 1, P) % P
+    h0 = 3 * pow(z, -1, P) % P
+    s = [0] * n
+    for off, wgt in weights.items():
+        s[off % n] = (s[off % n] + wgt * pow(g, -off, P)) % P
+    ginv = pow(g, -1, P)
+    B = [sum(s[o] * pow(ginv, o * k, P) for o in range(n) if s[o]) % P for k in range(n)]
+    D = [c0 * pow(h0, k, P) % P * B[k] % P for k in range(n)]
+    return [sum(D[k] * pow(g, i * k, P) for k in range(n)) % P for i in range(n)]
+
+
+def test_pole_sums_are_polynomials_on_the_coset():
+    """the identity behind the transform form of the DEEP quotient: on 3<g>, sum_off w_off / (x - z g^off) equals a polynomial whose
+    coefficients are C z^(n-1) (3/z)^k B[k] — checked against the definition for several pole sets (incl. offsets >= n, duplicates)."""
+    import random
+
+    rnd = random.Random(21)
+    for log_n in (3, 5):
+        n = 1 << log_n
+        g = pow(3, (P - 1) // n, P)
+        z = rnd.randrange(P)
+        for offs in ([0], [1, 5], [0, 2, 3, n + 1, 7], list(range(n))):
+            weights = {o: rnd.randrange(P) for o in offs}
+            got = _pole_sum_by_transforms(weights, z, n, g)
+            for i in range(n):
+                x = 3 * pow(g, i, P) % P
+                want = sum(wgt * pow((x - z * pow(g, o, P)) % P, -1, P) for o, wgt in weights.items()) % P
+                assert got[i] == want, (log_n, offs, i)
+
+
+def test_filtered_deep_program_matches_definition():
+    """deep_expr_filtered (V and the tap-heavy columns' W_c read from precomputed columns holding the pole sums, the other
+    columns' poles as shifted reads of u) == the definition of the DEEP quotient on the sub-coset rows, through the emulator of the
+    device interpreter; the pole-sum columns are filled by the transform identity above."""
+    import random
+
+    from sandstorm_b200.air import compile_template
+    from sandstorm_b200.air.deep import deep_expr_filtered, deep_filter_columns
+
+    rnd = random.Random(4)
+    log_n, b = 4, 1
+    n, N = 1 << log_n, 1 << (log_n + b)
+    g, w = pow(3, (P - 1) // n, P), pow(3, (P - 1) // N, P)
+    ncol, ce = 3, 2
+    lde = [[rnd.randrange(P) for _ in range(N)] for _ in range(ncol + ce)]
+    z, alpha = rnd.randrange(P), rnd.randrange(P)
+    zc = pow(z, ce, P)
+    taps = [(0, 0), (0, 1), (1, 0), (1, 1), (1, 2), (1, 5), (1, 7), (2, 3)]                  # column 1 is "heavy" at min_taps = 4
+    assert deep_filter_columns(taps, 4) == [1]
+    ood = [rnd.randrange(P) for _ in taps] + [rnd.randrange(P) for _ in range(ce)]
+    u_col, v_col, value_col, f_col = ncol + ce, ncol + ce + 1, ncol + ce + 2, ncol + ce + 3
+    tpl = compile_template(deep_expr_filtered(taps, ce, ncol, u_col, v_col, g, P, {1: f_col}, value_col), log_n, b, 1, len(taps) + ce, 1)
+    prog = tpl.patch([alpha], ood, [0])
+    u = [pow(3 * pow(w, i, P) - z, -1, P) for i in range(N)]
+    v = [pow(3 * pow(w, i, P) - zc, -1, P) for i in range(N)]
+    v_w, c_w, a = {}, {}, 1
+    for (col, off), y in zip(taps, ood):
+        v_w[off] = (v_w.get(off, 0) + a * y) % P
+        if col == 1:
+            c_w[off] = (c_w.get(off, 0) + a) % P
+        a = a * alpha % P
+    V, W1 = [0] * N, [0] * N
+    V[::2] = _pole_sum_by_transforms(v_w, z, n, g)                                            # rows i << b of the working matrix
+    W1[::2] = _pole_sum_by_transforms(c_w, z, n, g)
+    for i in range(0, N, 2):
+        x = 3 * pow(w, i, P) % P
+        want, a = 0, 1
+        for (col, off), y in zip(taps, ood):
+            want = (want + a * (lde[col][i] - y) * pow(x - z * pow(g, off, P), -1, P)) % P
+            a = a * alpha % P
+        for j in range(ce):
+            want = (want + a * (lde[ncol + j][i] - ood[len(taps) + j]) * pow(x - zc, -1, P)) % P
+            a = a * alpha % P
+        assert run_blob(prog.blob, i, lde + [u, v, V, W1], log_n + b) == want

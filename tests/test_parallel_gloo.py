@@ -294,3 +294,81 @@ def test_row_sharded_transforms_match_the_single_process_definitions(oracle, wor
             for j2 in range(m):
                 i = rank + world * j2
                 assert got[int(f"{j2:0{bits}b}"[::-1], 2) if bits else 0] == coeffs[2 * i + e] * pow(3, i, P) % P
+
+
+# ---- the transform pairs of the OOD / DEEP stages (prover._pole_sums_on_coset and the tap-heavy OOD columns), sharded ---------------
+def _pole_worker(rank, world, port, log_n, weights, z, trace_np, q):
+    from sandstorm_b200 import parallel
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        P = BigIntShardOps.P
+        ops = BigIntShardOps()
+        st = parallel.ShardedTransforms(rank, world, ops, "cpu")
+        n = 1 << log_n
+        g = pow(3, (P - 1) // n, P)
+        log_w = world.bit_length() - 1
+        # (1) pole sums: sparse weights w_off g^-off, c0 = C z^(n-1), h0 = 3/z, no expansion  (prover._pole_sums_on_coset, world > 1)
+        K, zn = pow(3, n, P), pow(z, n, P)
+        c0 = pow((K - zn) % P, -1, P) * pow(z, n - 1, P) % P
+        h0 = 3 * pow(z, -1, P) % P
+        buf = torch.full((n, 4), -1, dtype=torch.int64)
+        for lo, cnt in parallel.pieces(log_n, rank, world):
+            buf[lo:lo + cnt].zero_()
+        acc = {}
+        for off, wgt in weights.items():
+            acc[off % n] = (acc.get(off % n, 0) + wgt * pow(g, -off, P)) % P
+        for o, v in acc.items():
+            ops._put(buf, o, [v])                        # (also outside the owned pieces: never read there)
+        share = st.to_coefficients(buf, log_n, c0 * pow(h0, rank, P) % P, pow(h0, world, P))
+        out = torch.full((n, 4), -1, dtype=torch.int64)
+        st.from_coefficients(share, log_n - log_w, 0, out)
+        # (2) out-of-domain values of a tap-heavy column: T(z g^j) for every j  (prover._prove_sharded, heavy OOD columns)
+        t = torch.full((n, 4), -1, dtype=torch.int64)
+        full = torch.from_numpy(trace_np.view(np.int64))
+        for lo, cnt in parallel.pieces(log_n, rank, world):
+            t[lo:lo + cnt] = full[lo:lo + cnt]
+        share = st.to_coefficients(t, log_n, pow(n, -1, P) * pow(z, rank, P) % P, pow(z, world, P))
+        on_z = torch.full((n, 4), -1, dtype=torch.int64)
+        st.from_coefficients(share, log_n - log_w, 0, on_z)
+        q.put((rank, out.numpy().view(np.uint64).copy(), on_z.numpy().view(np.uint64).copy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,log_n", [(2, 4), (4, 5)])
+def test_sharded_pole_sums_and_coset_evaluation(oracle, world, log_n):
+    """The two transform pairs this round added to the sharded prover, over gloo with big-int local ops: every rank's owned
+    pieces of  sum_off w_off / (3 g^i - z g^off)  and of  T(z g^i)  equal the definitions."""
+    import random
+
+    from sandstorm_b200 import parallel
+
+    P = oracle.P
+    n = 1 << log_n
+    g = pow(3, (P - 1) // n, P)
+    rnd = random.Random(world * 10 + log_n)
+    z = rnd.randrange(P)
+    weights = {off: rnd.randrange(P) for off in (0, 1, 3, n - 1, n + 2)}
+    trace = oracle.random_felts(np.random.default_rng(log_n), 1, n)[0]
+    coeffs = oracle.from_mont(oracle.ntt(trace[None], inverse=True)[0])
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pole_worker, args=(r, world, port, log_n, weights, z, trace, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = {r: (a, b) for r, a, b in (q.get(timeout=120) for _ in procs)}
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, (poles, on_z) in results.items():
+        for lo, cnt in parallel.pieces(log_n, rank, world):
+            got_p, got_z = oracle.from_mont(poles[lo:lo + cnt]), oracle.from_mont(on_z[lo:lo + cnt])
+            for k in range(cnt):
+                i = lo + k
+                x = 3 * pow(g, i, P) % P
+                assert got_p[k] == sum(wgt * pow((x - z * pow(g, off, P)) % P, -1, P) for off, wgt in weights.items()) % P, (rank, i)
+                pt = z * pow(g, i, P) % P
+                assert got_z[k] == sum(c * pow(pt, e, P) for e, c in enumerate(coeffs)) % P, (rank, i)
