@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(256) poly_fold_kernel(const EvalJob *jobs, uns
 // ---- out[i] = 1 / (h * w_N^i - c) for every i: Montgomery batch inversion, R rows per thread ----------
 // Every denominator X - c * g^e of the AIR boundary terms and of the DEEP quotients is a shifted read of
 // this one vector:  x_i - c g^e = g^e (x_{i - b e} - c)  (g = w_N^b generates the trace domain).
-constexpr int INV_ROWS = 16;
+constexpr int INV_ROWS = 64;           // elements per thread, walked sequentially (prefix products parked in the output buffer)
 constexpr int INV_THREADS = 128;
 
 // Inverse of every thread's value with ONE field inversion per block (Montgomery's trick as a product tree in
@@ -159,37 +159,52 @@ __device__ __forceinline__ Fp block_inverse(const Fp &v, Fp *sm) {
     }
     return sm[INV_THREADS + tid];
 }
+// Two sweeps per thread over its INV_ROWS elements with ONE inversion per block of INV_THREADS * INV_ROWS = 8192 elements:
+// forward, the running product before each element is parked in the element's own output slot; after the block inversion the
+// backward sweep recomputes the element (a table product), reads its prefix back and writes the inverse.  No per-thread arrays:
+// few registers, many resident blocks, so the serial a^(p-2) chain of one block hides under the sweeps of the others (the
+// previous form held 16 elements + 16 prefixes in 255 registers, two blocks per SM, and spent 80 % of its time in that chain).
+template <typename ElemFn>
+__device__ __forceinline__ void batch_invert_block(Fp *out, unsigned long long count, ElemFn elem, Fp *sm) {
+    const unsigned long long chunk = (unsigned long long)blockDim.x * INV_ROWS;
+    const unsigned long long base = blockIdx.x * chunk + threadIdx.x;
+    Fp acc = fp::one();
+#pragma unroll 1
+    for (int k = 0; k < INV_ROWS; ++k) {
+        const unsigned long long t = base + (unsigned long long)k * blockDim.x;
+        if (t < count) {
+            unsigned long long slot;
+            const Fp x = elem(t, slot);
+            st_fp(out + slot, acc);
+            acc = fp::mul(acc, x);
+        }
+    }
+    Fp inv = block_inverse(acc, sm);
+#pragma unroll 1
+    for (int k = INV_ROWS - 1; k >= 0; --k) {
+        const unsigned long long t = base + (unsigned long long)k * blockDim.x;
+        if (t < count) {
+            unsigned long long slot;
+            const Fp x = elem(t, slot);
+            const Fp r = fp::mul(inv, ld_fp(out + slot));
+            inv = fp::mul(inv, x);
+            st_fp(out + slot, fp::canon(r));
+        }
+    }
+}
+
 __global__ void __launch_bounds__(INV_THREADS) inv_x_minus_c_kernel(Fp *out, int log_n, int log_step, unsigned long long first, unsigned long long count, Fp c,
                                                                       const Fp *xlo, const Fp *xhi) {
     __shared__ Fp sm[2 * INV_THREADS];
     const unsigned long long mask = (1ull << log_n) - 1;
-    const unsigned long long chunk = (unsigned long long)blockDim.x * INV_ROWS;
-    const unsigned long long base = blockIdx.x * chunk + threadIdx.x;     // rows ((first + base + k * blockDim.x) << log_step) mod N
-    Fp d[INV_ROWS], pre[INV_ROWS];
-    Fp acc = fp::one();
-#pragma unroll
-    for (int k = 0; k < INV_ROWS; ++k) {
-        const unsigned long long t = base + (unsigned long long)k * blockDim.x;
+    // element t = row ((first + t) << log_step) mod N: x_i - c, x_i = h w_N^i from two tables
+    batch_invert_block(out, count, [&](unsigned long long t, unsigned long long &slot) {
         const unsigned long long i = ((first + t) << log_step) & mask;
-        Fp x = fp::one();
-        if (t < count) {
-            x = ld_fp(xlo + (i & 4095ull));
-            if (i >> 12) x = fp::mul(x, ld_fp(xhi + (i >> 12)));
-            x = fp::sub(x, c);
-        }
-        d[k] = x;
-        pre[k] = acc;
-        acc = fp::mul(acc, x);
-    }
-    Fp inv = block_inverse(acc, sm);
-#pragma unroll
-    for (int k = INV_ROWS - 1; k >= 0; --k) {
-        const unsigned long long t = base + (unsigned long long)k * blockDim.x;
-        const unsigned long long i = ((first + t) << log_step) & mask;
-        const Fp r = fp::mul(inv, pre[k]);
-        inv = fp::mul(inv, d[k]);
-        if (t < count) st_fp(out + i, fp::canon(r));
-    }
+        slot = i;
+        Fp x = ld_fp(xlo + (i & 4095ull));
+        if (i >> 12) x = fp::mul(x, ld_fp(xhi + (i >> 12)));
+        return fp::sub(x, c);
+    }, sm);
 }
 
 // ---- out-of-domain evaluation from the trace itself (barycentric form) ------------------------------------
@@ -204,32 +219,13 @@ __global__ void __launch_bounds__(INV_THREADS) inv_x_minus_c_kernel(Fp *out, int
 __global__ void __launch_bounds__(INV_THREADS) bary_weights_kernel(Fp *out, unsigned long long row_begin, unsigned long long count, Fp z,
                                                                      const Fp *ginv_lo, const Fp *ginv_hi) {
     __shared__ Fp sm[2 * INV_THREADS];
-    const unsigned long long chunk = (unsigned long long)blockDim.x * INV_ROWS;
-    const unsigned long long base = blockIdx.x * chunk + threadIdx.x;
-    Fp d[INV_ROWS], pre[INV_ROWS];
-    Fp acc = fp::one();
-#pragma unroll
-    for (int k = 0; k < INV_ROWS; ++k) {
-        const unsigned long long t = base + (unsigned long long)k * blockDim.x;
-        Fp x = fp::one();
-        if (t < count) {
-            const unsigned long long j = row_begin + t;
-            x = ld_fp(ginv_lo + (j & 4095ull));
-            if (j >> 12) x = fp::mul(x, ld_fp(ginv_hi + (j >> 12)));
-            x = fp::sub(fp::mul(x, z), fp::one());
-        }
-        d[k] = x;
-        pre[k] = acc;
-        acc = fp::mul(acc, x);
-    }
-    Fp inv = block_inverse(acc, sm);
-#pragma unroll
-    for (int k = INV_ROWS - 1; k >= 0; --k) {
-        const unsigned long long t = base + (unsigned long long)k * blockDim.x;
-        const Fp r = fp::mul(inv, pre[k]);
-        inv = fp::mul(inv, d[k]);
-        if (t < count) st_fp(out + t, fp::canon(r));
-    }
+    batch_invert_block(out, count, [&](unsigned long long t, unsigned long long &slot) {
+        const unsigned long long j = row_begin + t;
+        slot = t;
+        Fp x = ld_fp(ginv_lo + (j & 4095ull));
+        if (j >> 12) x = fp::mul(x, ld_fp(ginv_hi + (j >> 12)));
+        return fp::sub(fp::mul(x, z), fp::one());
+    }, sm);
 }
 
 // ood_dot_kernel: block (x = tap pair, y = row chunk) accumulates  sum_j t[(j + off) mod n] * W_j  over its chunk
