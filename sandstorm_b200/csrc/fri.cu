@@ -123,8 +123,14 @@ __global__ void __launch_bounds__(256) poly_fold_kernel(const EvalJob *jobs, uns
 // ---- out[i] = 1 / (h * w_N^i - c) for every i: Montgomery batch inversion, R rows per thread ----------
 // Every denominator X - c * g^e of the AIR boundary terms and of the DEEP quotients is a shifted read of
 // this one vector:  x_i - c g^e = g^e (x_{i - b e} - c)  (g = w_N^b generates the trace domain).
-constexpr int INV_ROWS = 64;           // elements per thread, walked sequentially (prefix products parked in the output buffer)
+constexpr int INV_ROWS = 64;           // most elements per thread, walked sequentially (prefix products parked in the output buffer)
 constexpr int INV_THREADS = 128;
+// elements per thread for a launch over `count` elements: long sweeps amortise the block's one inversion, but a short vector
+// (one rank's piece) must still fill the GPU with blocks
+static int inv_rows_for(unsigned long long count) {
+    const unsigned long long want = count / ((unsigned long long)INV_THREADS * 148 * 8) + 1;
+    return want >= INV_ROWS ? INV_ROWS : (want < 8 ? 8 : (int)want);
+}
 
 // Inverse of every thread's value with ONE field inversion per block (Montgomery's trick as a product tree in
 // shared memory): up-sweep of pairwise products, thread 0 inverts the root (a^(p-2): 250 squarings + 11
@@ -165,12 +171,12 @@ __device__ __forceinline__ Fp block_inverse(const Fp &v, Fp *sm) {
 // few registers, many resident blocks, so the serial a^(p-2) chain of one block hides under the sweeps of the others (the
 // previous form held 16 elements + 16 prefixes in 255 registers, two blocks per SM, and spent 80 % of its time in that chain).
 template <typename ElemFn>
-__device__ __forceinline__ void batch_invert_block(Fp *out, unsigned long long count, ElemFn elem, Fp *sm) {
-    const unsigned long long chunk = (unsigned long long)blockDim.x * INV_ROWS;
+__device__ __forceinline__ void batch_invert_block(Fp *out, unsigned long long count, int rows, ElemFn elem, Fp *sm) {
+    const unsigned long long chunk = (unsigned long long)blockDim.x * rows;
     const unsigned long long base = blockIdx.x * chunk + threadIdx.x;
     Fp acc = fp::one();
 #pragma unroll 1
-    for (int k = 0; k < INV_ROWS; ++k) {
+    for (int k = 0; k < rows; ++k) {
         const unsigned long long t = base + (unsigned long long)k * blockDim.x;
         if (t < count) {
             unsigned long long slot;
@@ -181,7 +187,7 @@ __device__ __forceinline__ void batch_invert_block(Fp *out, unsigned long long c
     }
     Fp inv = block_inverse(acc, sm);
 #pragma unroll 1
-    for (int k = INV_ROWS - 1; k >= 0; --k) {
+    for (int k = rows - 1; k >= 0; --k) {
         const unsigned long long t = base + (unsigned long long)k * blockDim.x;
         if (t < count) {
             unsigned long long slot;
@@ -193,12 +199,12 @@ __device__ __forceinline__ void batch_invert_block(Fp *out, unsigned long long c
     }
 }
 
-__global__ void __launch_bounds__(INV_THREADS) inv_x_minus_c_kernel(Fp *out, int log_n, int log_step, unsigned long long first, unsigned long long count, Fp c,
+__global__ void __launch_bounds__(INV_THREADS) inv_x_minus_c_kernel(Fp *out, int log_n, int log_step, unsigned long long first, unsigned long long count, int rows, Fp c,
                                                                       const Fp *xlo, const Fp *xhi) {
     __shared__ Fp sm[2 * INV_THREADS];
     const unsigned long long mask = (1ull << log_n) - 1;
     // element t = row ((first + t) << log_step) mod N: x_i - c, x_i = h w_N^i from two tables
-    batch_invert_block(out, count, [&](unsigned long long t, unsigned long long &slot) {
+    batch_invert_block(out, count, rows, [&](unsigned long long t, unsigned long long &slot) {
         const unsigned long long i = ((first + t) << log_step) & mask;
         slot = i;
         Fp x = ld_fp(xlo + (i & 4095ull));
@@ -216,10 +222,10 @@ __global__ void __launch_bounds__(INV_THREADS) inv_x_minus_c_kernel(Fp *out, int
 // splits over row ranges (one per GPU).
 //
 // bary_weights_kernel: W_j for j in [row_begin, row_begin + count), Montgomery batch inversion per thread.
-__global__ void __launch_bounds__(INV_THREADS) bary_weights_kernel(Fp *out, unsigned long long row_begin, unsigned long long count, Fp z,
+__global__ void __launch_bounds__(INV_THREADS) bary_weights_kernel(Fp *out, unsigned long long row_begin, unsigned long long count, int rows, Fp z,
                                                                      const Fp *ginv_lo, const Fp *ginv_hi) {
     __shared__ Fp sm[2 * INV_THREADS];
-    batch_invert_block(out, count, [&](unsigned long long t, unsigned long long &slot) {
+    batch_invert_block(out, count, rows, [&](unsigned long long t, unsigned long long &slot) {
         const unsigned long long j = row_begin + t;
         slot = t;
         Fp x = ld_fp(ginv_lo + (j & 4095ull));
@@ -401,12 +407,13 @@ ss_status ss_inv_x_minus_c(ss_ctx *ctx, ss_field field, int log_n, int log_row_s
     // x_i = 3 * w_N^i: same tables (and cache keys) as the constraint evaluator's OP_X
     if ((rc = cached_table(ctx, {20, log_n, 0}, n < 4096 ? n : 4096, [](Fp *d, size_t m, int ln, int) { fill_x_lo(d, m, ln, 3); }, &lo))) return rc;
     if ((rc = cached_table(ctx, {21, log_n, 0}, n <= 4096 ? 1 : n / 4096, fill_x_hi, &hi))) return rc;
-    const unsigned long long chunk = (unsigned long long)INV_THREADS * INV_ROWS;
     // rows (row_begin + t) << step, t < row_count, wrapping mod N (a rank's row range plus the halo its shifted reads need)
     if (row_count == 0) { row_begin = 0; row_count = n >> log_row_step; }
     if (row_count > (n >> log_row_step)) return fail(ctx, SS_ERR_INVALID, "ss_inv_x_minus_c: row range larger than the domain");
+    const int rows = inv_rows_for(row_count);
+    const unsigned long long chunk = (unsigned long long)INV_THREADS * rows;
     inv_x_minus_c_kernel<<<(unsigned)((row_count + chunk - 1) / chunk), INV_THREADS, 0, pick_stream(ctx, stream)>>>(
-        static_cast<Fp *>(d_out), log_n, log_row_step, row_begin, row_count, fp::canon(load_host(h_c)), lo, hi);
+        static_cast<Fp *>(d_out), log_n, log_row_step, row_begin, row_count, rows, fp::canon(load_host(h_c)), lo, hi);
     ctx->launches++;
     SS_CUDA_CHECK(ctx, cudaGetLastError());
     return SS_OK;
@@ -475,8 +482,9 @@ ss_status ss_ood_eval(ss_ctx *ctx, ss_field field, const void *d_trace_cols, uin
     if (ce != cudaSuccess) { cleanup(); return fail(ctx, SS_ERR_OOM, "ss_ood_eval: %s", cudaGetErrorString(ce)); }
     cudaMemcpy(d_taps, taps.data(), taps.size() * sizeof(OodTap), cudaMemcpyHostToDevice);
     cudaMemcpy(d_where, where.data(), n_evals * sizeof(int2), cudaMemcpyHostToDevice);
-    const unsigned long long wchunk = (unsigned long long)INV_THREADS * INV_ROWS;
-    bary_weights_kernel<<<(unsigned)((row_count + wchunk - 1) / wchunk), INV_THREADS>>>(d_w, row_begin, row_count, z, lo, hi);
+    const int wrows = inv_rows_for(row_count);
+    const unsigned long long wchunk = (unsigned long long)INV_THREADS * wrows;
+    bary_weights_kernel<<<(unsigned)((row_count + wchunk - 1) / wchunk), INV_THREADS>>>(d_w, row_begin, row_count, wrows, z, lo, hi);
     if ((unsigned long long)taps.size() * n_chunks > 0x7fffffffull) { cleanup(); return fail(ctx, SS_ERR_UNSUPPORTED, "ss_ood_eval: grid too large"); }
     ood_dot_kernel<<<(unsigned)(taps.size() * n_chunks), OOD_THREADS>>>(static_cast<const Fp *>(d_trace_cols), col_stride, log_n, d_w, row_begin,
                                                                            row_count, d_taps, (unsigned)taps.size(), n_chunks, d_part);
