@@ -231,6 +231,13 @@ class HotPathProver:
         h0 = 3 * pow(z, -1, P) % P
         W, r = self.world, self.rank
         mine = pieces(log_n, r, W) if W > 1 else [(0, n)]
+        cache = self.__dict__.setdefault("_ginv_pow", {})          # g^-off per mask offset: layout constants, computed once
+
+        def ginv(off):
+            v = cache.get(off)
+            if v is None:
+                v = cache[off] = pow(g, -off, P)
+            return v
         from .parallel import ShardedTransforms
 
         buf = torch.empty((n, 4), dtype=torch.int64, device=dev)
@@ -242,7 +249,7 @@ class HotPathProver:
         for weights, out in jobs:
             acc: dict[int, int] = {}
             for off, w in weights.items():
-                acc[off % n] = (acc.get(off % n, 0) + w * pow(g, -off, P)) % P
+                acc[off % n] = (acc.get(off % n, 0) + w * ginv(off)) % P
             idx = torch.tensor(sorted(acc), dtype=torch.int64, device=dev)
             vals = torch.from_numpy(np.stack([_mont(acc[o]) for o in sorted(acc)]).view(np.int64)).to(dev)
             for lo, cnt in mine:
