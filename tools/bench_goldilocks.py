@@ -1,3 +1,8 @@
+#!/usr/bin/env python3
+"""Goldilocks NTT timing on one GPU (run on the GPU box): forward DIF (natural -> bit-reversed) + inverse DIT (bit-reversed ->
+natural, with its 1/n sweep), averaged, for 2^20 x 64, 2^24 x 8 and 2^26 x 4 columns.  Prints field-ops/s (1.5 n log n per
+transform) and the read-once / write-once GB/s the roofline fraction in DESIGN.md §4.7 is quoted on.
+    gpurun -- python tools/bench_goldilocks.py"""
 import torch, time, sys
 sys.path.insert(0, '/root/repo')
 import sandstorm_b200 as ss
