@@ -3,8 +3,12 @@
 natural, with its 1/n sweep), averaged, for 2^20 x 64, 2^24 x 8 and 2^26 x 4 columns.  Prints field-ops/s (1.5 n log n per
 transform) and the read-once / write-once GB/s the roofline fraction in DESIGN.md §4.7 is quoted on.
     gpurun -- python tools/bench_goldilocks.py"""
-import torch, time, sys
-sys.path.insert(0, '/root/repo')
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import sandstorm_b200 as ss
 from sandstorm_b200 import goldilocks as glk
 for log_n, cols in ((20, 64), (24, 8), (26, 4)):
